@@ -1,0 +1,105 @@
+/* zk_msm_b200.h -- C ABI of libzkmsm_b200.so: B200 (sm_100a) G1 multi-scalar multiplication for
+ * BN254 ("bn128") and BLS12-381, a drop-in for the MSM entry points of bkomuves/zikkurat-algebra's
+ * generated C library.  Plain pointers and sizes only; there is NO CPU fallback: every entry point
+ * needs a CUDA device and aborts (message on stderr + abort(), the reference's own convention for
+ * malloc failure: lib/cbits/curves/g1/proj/bn128_G1_proj.c:516-517,630-631) when CUDA fails.
+ *
+ * Memory layouts are the reference's:
+ *   scalars  npoints x expo_nlimbs little-endian uint64 limbs; "std" = plain integer (any value
+ *            < 2^(64*expo_nlimbs) is accepted), "mont" = k * 2^256 mod r (expo_nlimbs must be 4)
+ *   points   npoints x (x || y), Fp coordinates in Montgomery form, 4 (bn128) or 6 (bls12_381)
+ *            uint64 limbs each; the point at infinity is the all-0xFF record
+ *   result   proj  (X:Y:Z)  3 coordinates, infinity = (0, R mod p, 0)
+ *            jac   (X:Y:Z)  3 coordinates, x = X/Z^2, y = Y/Z^3, infinity = (R, R, 0) mod p
+ *            affine (x || y), canonical, infinity = all 0xFF   <- bit-identical to the reference
+ * proj/jac results are valid representatives accepted by the reference's *_to_affine / *_is_infinity
+ * (they are not the same representative the reference's operation order would produce).
+ * expo_nlimbs: 1..4 supported (the Haskell bindings always pass 4: .../BN128/G1/Proj.hs:245,262).
+ */
+#ifndef ZK_MSM_B200_H
+#define ZK_MSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- the reference's symbols (same names, same signatures) -------------------------------------
+ * replaces lib/cbits/curves/g1/proj/bn128_G1_proj.h:43-46  (definitions bn128_G1_proj.c:596-669) */
+void bn128_G1_proj_MSM_std_coeff_proj_out   (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G1_proj_MSM_mont_coeff_proj_out  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G1_proj_MSM_std_coeff_affine_out (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G1_proj_MSM_mont_coeff_affine_out(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+/* replaces lib/cbits/curves/g1/jac/bn128_G1_jac.h:43-46  (definitions bn128_G1_jac.c:645-718) */
+void bn128_G1_jac_MSM_std_coeff_jac_out     (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G1_jac_MSM_mont_coeff_jac_out    (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G1_jac_MSM_std_coeff_affine_out  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G1_jac_MSM_mont_coeff_affine_out (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+/* replaces lib/cbits/curves/g1/proj/bls12_381_G1_proj.h:43-46 (definitions bls12_381_G1_proj.c:597-670) */
+void bls12_381_G1_proj_MSM_std_coeff_proj_out   (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_proj_MSM_mont_coeff_proj_out  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_proj_MSM_std_coeff_affine_out (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_proj_MSM_mont_coeff_affine_out(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+/* replaces lib/cbits/curves/g1/jac/bls12_381_G1_jac.h:43-46 (definitions bls12_381_G1_jac.c:646-719) */
+void bls12_381_G1_jac_MSM_std_coeff_jac_out     (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_jac_MSM_mont_coeff_jac_out    (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_jac_MSM_std_coeff_affine_out  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_jac_MSM_mont_coeff_affine_out (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+
+/* The un-prototyped but exported "_variable" definitions (bn128_G1_proj.c:506, bn128_G1_jac.c:555 and
+ * twins).  window_size is honoured as OUR signed-digit window width c (clamped to [1,24]); the
+ * reference asserts 1 <= window_size <= 64 (bn128_G1_proj.c:508). */
+void bn128_G1_proj_MSM_std_coeff_proj_out_variable    (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs, int window_size);
+void bn128_G1_jac_MSM_std_coeff_jac_out_variable      (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs, int window_size);
+void bls12_381_G1_proj_MSM_std_coeff_proj_out_variable(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs, int window_size);
+void bls12_381_G1_jac_MSM_std_coeff_jac_out_variable  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs, int window_size);
+
+/* ---- extensions (not in the reference) -------------------------------------------------------- */
+enum { ZKB200_BN128 = 0, ZKB200_BLS12_381 = 1 };
+enum { ZKB200_OUT_PROJ = 0, ZKB200_OUT_JAC = 1, ZKB200_OUT_AFFINE = 2, ZKB200_OUT_XYZZ = 3 };
+enum { ZKB200_HOST = 0, ZKB200_DEVICE = 1 };
+
+/* Generic entry point behind all of the above.  nmsm independent MSMs of npoints each over ONE shared
+ * point array (SURVEY.md section 8b "batch" extension; KZG commitments over a shared SRS):
+ *   scalars  nmsm x npoints x expo_nlimbs limbs,  out  nmsm records of (2|3|4) coordinates.
+ * scalars_loc / points_loc say whether the pointer is host or device (current device) memory; `out` is
+ * always host memory.  window = 0 picks the tuned window width. */
+void zkb200_msm(int curve, int nmsm, long npoints, const uint64_t *scalars, int scalars_loc,
+                const uint64_t *points, int points_loc, int expo_nlimbs, int mont_coeff, int out_mode,
+                int window, uint64_t *out);
+
+/* Sum of k group elements (multi-GPU combine of partial MSM results): in_mode / out_mode as above
+ * (in_mode: PROJ, JAC or XYZZ records in host memory). */
+void zkb200_sum_points(int curve, int k, const uint64_t *in, int in_mode, int out_mode, uint64_t *out);
+
+/* Workload synthesis on the GPU (not part of the MSM path): out[i] = P0 + (start + i) * D for
+ * i < n as canonical affine Montgomery points, written to host (out_loc = ZKB200_HOST) or device memory.
+ * Used by bench.py and the tests to build large synthetic point arrays. */
+void zkb200_gen_chain(int curve, unsigned long long start, long n, const uint64_t *p0_affine,
+                      const uint64_t *d_affine, uint64_t *out, int out_loc);
+
+/* Number of kernels this library has launched since it was loaded (bench.py's "gpu_launches"). */
+long long zkb200_launch_count(void);
+
+/* Device used by subsequent calls of the calling process (default: $ZKB200_DEVICE or 0). */
+void zkb200_set_device(int device);
+
+/* Phase timings (CUDA events, ms) of the most recent zkb200_msm on this thread's device:
+ *  [0] h2d scalars  [1] recode  [2] sort  [3] wait for points h2d  [4] accumulate  [5] fixup
+ *  [6] reduce  [7] tail + d2h   [8] total on the compute stream.
+ * Also: window width c, number of windows W, insertions n*W, of the same call. */
+void zkb200_last_stats(float phase_ms[9], int *window_c, int *nwindows, long long *insertions);
+
+/* Register-resident integer-multiply throughput probe: returns 32x32-bit products per second of the
+ * whole GPU for kind 0 = mad.lo/madc.hi carry chains (as used by the field code), 1 = mad.wide.u32,
+ * 2 = mad.lo.u32 only.  Used for the IMAD roofline denominator. */
+double zkb200_imad_peak(int kind, int iters);
+
+const char *zkb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""Limb-level device algorithms (fp.cuh / ec.cuh / recode.cuh) compiled for the HOST with emulated
+carry-chain primitives, checked against the Python big-int model and the C oracles.  No GPU needed.
+Mirrors the reference's fast-vs-reference field tests (test/src/ZK/Test/Field/AgainstRef.hs:25-60)
+and the curve edge cases of test/src/ZK/Test/Curve/Properties.hs:425-483."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import pyec, refs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "host_emul.cpp")
+SO = os.path.join(HERE, "host_emul", "libhost_emul.so")
+CSRC = os.path.join(refs.ROOT, "zikkurat_algebra_b200", "csrc")
+CURVES = ["bn128", "bls12_381"]
+
+
+@pytest.fixture(scope="module")
+def he():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("hd.cuh", "fp.cuh", "ec.cuh", "recode.cuh", "curve_params.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", f"-I{CSRC}", SRC, "-o", SO], check=True)
+    return ctypes.CDLL(SO)
+
+
+def _arr(bs):
+    return np.frombuffer(bs, dtype=np.uint64).copy()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_fp_ops(he, curve):
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    rng = random.Random(11)
+    edge = [0, 1, 2, cv.p - 1, cv.p - 2, cv.R % cv.p, (1 << (32 * (2 * L - 1))) % cv.p, (cv.p - 1) // 2]
+    vals = [(a, b) for a in edge for b in edge] + [(rng.randrange(cv.p), rng.randrange(cv.p)) for _ in range(2000)]
+    Rinv = pow(cv.R, -1, cv.p)
+    for a, b in vals:
+        # raw Montgomery residues a, b (any canonical value is a valid encoding)
+        A, B = _arr(a.to_bytes(8 * L, "little")), _arr(b.to_bytes(8 * L, "little"))
+        dec = lambda x: int.from_bytes(x.tobytes(), "little")
+        assert dec(refs.call3(he, f"he_{curve}_fp_mul", A, B, L)) == a * b * Rinv % cv.p
+        assert dec(refs.call3(he, f"he_{curve}_fp_add", A, B, L)) == (a + b) % cv.p
+        assert dec(refs.call3(he, f"he_{curve}_fp_sub", A, B, L)) == (a - b) % cv.p
+        assert dec(refs.call2(he, f"he_{curve}_fp_neg", A, L)) == (-a) % cv.p
+    for a in [1, 2, cv.p - 1] + [rng.randrange(1, cv.p) for _ in range(20)]:
+        A = _arr(cv.fp_to_bytes(a))
+        assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv", A, L).tobytes()) == pow(a, -1, cv.p)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_fp_mul_matches_oracle_bytes(he, curve):
+    L = refs.CURVE_LIMBS[curve]
+    cv = pyec.CURVES[curve]
+    rng = random.Random(5)
+    for _ in range(500):
+        A = _arr(rng.randrange(cv.p).to_bytes(8 * L, "little"))
+        B = _arr(rng.randrange(cv.p).to_bytes(8 * L, "little"))
+        want = refs.call3(refs.oracle(), f"zko_{curve}_Fp_mont_mul", A, B, L)
+        assert refs.call3(he, f"he_{curve}_fp_mul", A, B, L).tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_fr_to_std(he, curve):
+    cv = pyec.CURVES[curve]
+    rng = random.Random(3)
+    for k in [0, 1, cv.r - 1] + [rng.randrange(cv.r) for _ in range(200)]:
+        enc = _arr(k.to_bytes(32, "little"))
+        got = int.from_bytes(refs.call2(he, f"he_{curve}_fr_to_std", enc, 4).tobytes(), "little")
+        assert got == k * pow(cv.Rr, -1, cv.r) % cv.r
+
+
+def _sum_list(he, curve, pts, negs=None):
+    cv = pyec.CURVES[curve]
+    f = getattr(he, f"he_{curve}_sum_list")
+    f.argtypes = [ctypes.c_long, refs.U64P, ctypes.c_char_p, refs.U64P]
+    f.restype = None
+    P = _arr(cv.points_to_bytes(pts)) if pts else np.zeros(1, np.uint64)
+    out = np.zeros(2 * cv.nlimbs_p, np.uint64)
+    f(len(pts), refs.ptr(P), bytes(negs) if negs is not None else None, refs.ptr(out))
+    return out.tobytes()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_bucket_sums_with_exceptional_cases(he, curve):
+    cv = pyec.CURVES[curve]
+    G = cv.gen
+    P, Q = cv.mul(5, G), cv.mul(77, G)
+    rng = random.Random(9)
+    lists = [
+        [], [P], [P, P], [P, cv.neg(P)], [P, cv.neg(P), Q], [P, P, P, P, P], [None, P, None, Q],
+        [P, Q, cv.neg(cv.add(P, Q))], [P, Q, cv.add(P, Q)], [cv.mul(2, P), P, P],
+        pyec.chain_points(cv, 40, 3, 5),
+    ]
+    for pts in lists:
+        assert _sum_list(he, curve, pts) == cv.affine_to_bytes(cv.msm([1] * len(pts), pts))
+        negs = [rng.randrange(2) for _ in pts]
+        want = cv.affine_to_bytes(cv.msm([-1 if s else 1 for s in negs], pts))
+        assert _sum_list(he, curve, pts, negs) == want
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_full_add_and_output_representations(he, curve):
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    G = cv.gen
+    P, Q = cv.mul(5, G), cv.mul(77, G)
+    f = getattr(he, f"he_{curve}_add_lists")
+    f.argtypes = [ctypes.c_long, refs.U64P, ctypes.c_long, refs.U64P, refs.U64P, refs.U64P, refs.U64P]
+    f.restype = None
+    cases = [([P], [Q]), ([P, Q], [P, Q]), ([P, Q], [cv.neg(P), cv.neg(Q)]), ([], [P]), ([P], []), ([], []),
+             ([P, P], [Q, G]), ([P, cv.neg(P)], [Q])]
+    for l1, l2 in cases:
+        a1 = _arr(cv.points_to_bytes(l1)) if l1 else np.zeros(1, np.uint64)
+        a2 = _arr(cv.points_to_bytes(l2)) if l2 else np.zeros(1, np.uint64)
+        aff, proj, jac = np.zeros(2 * L, np.uint64), np.zeros(3 * L, np.uint64), np.zeros(3 * L, np.uint64)
+        f(len(l1), refs.ptr(a1), len(l2), refs.ptr(a2), refs.ptr(aff), refs.ptr(proj), refs.ptr(jac))
+        want = cv.msm([1] * (len(l1) + len(l2)), l1 + l2)
+        assert aff.tobytes() == cv.affine_to_bytes(want)
+        assert cv.proj_from_bytes(proj.tobytes()) == want
+        assert cv.jac_from_bytes(jac.tobytes()) == want
+        if refs.have_ref():  # the reference's own predicates must accept our representatives
+            lib = refs.ref()
+            for rep, buf in (("proj", proj), ("jac", jac)):
+                g = getattr(lib, f"{curve}_G1_{rep}_is_infinity")
+                g.argtypes = [refs.U64P]
+                g.restype = ctypes.c_uint8
+                assert bool(g(refs.ptr(buf))) == (want is None)
+                assert refs.call2(lib, f"{curve}_G1_{rep}_to_affine", buf, 2 * L).tobytes() == cv.affine_to_bytes(want)
+
+
+def test_signed_digit_recoding(he):
+    rng = random.Random(4)
+    f = he.he_recode
+    f.argtypes = [refs.U64P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+    f.restype = None
+    for nbits in (254, 255, 256, 64, 128):
+        for c in (1, 2, 5, 8, 11, 13, 16, 17, 20, 23, 24):
+            nwin = (nbits + 1 + c - 1) // c
+            ks = [0, 1, (1 << nbits) - 1, 1 << (nbits - 1), (1 << (c - 1)), (1 << c) - 1] + [rng.randrange(1 << nbits) for _ in range(50)]
+            for k in ks:
+                keys = (ctypes.c_uint32 * (nwin + 1))()
+                negs = (ctypes.c_uint32 * (nwin + 1))()
+                f(refs.ptr(_arr(k.to_bytes(32, "little"))), nbits, c, nwin, keys, negs)
+                assert keys[nwin] == 0, "carry out of the top window"
+                tot = 0
+                for w in range(nwin):
+                    assert 0 <= keys[w] <= (1 << (c - 1))
+                    tot += (-keys[w] if negs[w] else keys[w]) << (c * w)
+                assert tot == k, (nbits, c, k)

@@ -1,0 +1,248 @@
+"""Parity tests proper (B200): the CUDA path, called through the C-ABI, against the CPU oracles.
+
+Bar: canonical affine output BIT-EXACT with the reference C (oracle/_ref, falling back to the pinned
+restatement oracle/libzk_oracle.so); proj/jac outputs equal as group elements after the reference's own
+*_to_affine.  Edge cases are the reference's: empty / tiny inputs, infinity inputs,
+P and -P, repeated points, un-reduced 256-bit scalars, zero scalars (section 8b, 8d).
+"""
+import ctypes
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests import pyec, refs
+
+pytestmark = pytest.mark.gpu
+
+CURVES = ["bn128", "bls12_381"]
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "msm_golden.json")))["vectors"]
+
+
+@pytest.fixture(scope="module")
+def zk():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    import zikkurat_algebra_b200 as z
+    from zikkurat_algebra_b200 import build
+    build.build()
+    z.lib()
+    return z
+
+
+def cpu_lib():
+    return (refs.ref(), "") if refs.have_ref() else (refs.oracle(), "zko_")
+
+
+def cpu_affine(curve, sc, pts, form="std", rep="proj", n=None):
+    lib, pre = cpu_lib()
+    L = refs.CURVE_LIMBS[curve]
+    n = sc.size // 4 if n is None else n
+    if n == 0:  # the shipped reference evaluates log2(0); infinity is the defined answer
+        return np.full(2 * L, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    return refs.call_msm(lib, f"{pre}{curve}_G1_{rep}_MSM_{form}_coeff_affine_out", sc.ravel(), pts.ravel(), 2 * L, n=n)
+
+
+def to_affine_cpu(curve, rep, buf):
+    lib, pre = cpu_lib()
+    return refs.call2(lib, f"{pre}{curve}_G1_{rep}_to_affine", buf, 2 * refs.CURVE_LIMBS[curve])
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 123, 1000, 5000])
+def test_all_reference_symbols(zk, curve, n):
+    L = refs.CURVE_LIMBS[curve]
+    pts = refs.chain_points(curve, n)
+    for form in ("std", "mont"):
+        sc = refs.random_scalars(curve, n, seed=n + 17, reduce=(form == "mont"))
+        want = cpu_affine(curve, sc, pts, form, n=n)
+        for rep in ("proj", "jac"):
+            got = zk.call_reference_symbol(f"{curve}_G1_{rep}_MSM_{form}_coeff_affine_out", sc, pts, npoints=n)
+            assert got.tobytes() == want.tobytes(), (curve, n, form, rep, "affine_out")
+            out = zk.call_reference_symbol(f"{curve}_G1_{rep}_MSM_{form}_coeff_{rep}_out", sc, pts, npoints=n)
+            assert to_affine_cpu(curve, rep, out).tobytes() == want.tobytes(), (curve, n, form, rep, "rep_out")
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_infinity_representations(zk, curve):
+    """n = 0 and all-zero scalars: proj (0,R,0), jac (R,R,0), affine 0xFF."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    one = np.frombuffer((cv.R % cv.p).to_bytes(cv.fp_bytes, "little"), dtype=np.uint64)
+    zero = np.zeros(L, np.uint64)
+    pts = refs.chain_points(curve, 4)
+    for n, sc in ((0, np.zeros((0, 4), np.uint64)), (4, np.zeros((4, 4), np.uint64))):
+        p = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_proj_out", sc, pts[:n], npoints=n)
+        assert p.tobytes() == np.concatenate([zero, one, zero]).tobytes()
+        j = zk.call_reference_symbol(f"{curve}_G1_jac_MSM_std_coeff_jac_out", sc, pts[:n], npoints=n)
+        assert j.tobytes() == np.concatenate([one, one, zero]).tobytes()
+        a = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts[:n], npoints=n)
+        assert a.tobytes() == b"\xff" * (16 * L)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_adversarial_inputs(zk, curve):
+    cv = pyec.CURVES[curve]
+    G = cv.gen
+    P = cv.mul(7, G)
+    Q = cv.mul(1234567, G)
+    top = (1 << 256) - 1
+    sets = {
+        "p_minus_p": ([5, 5], [P, cv.neg(P)]),
+        "p_minus_p_then_more": ([5, 5, 9], [P, cv.neg(P), Q]),
+        "repeated": ([3, 3, 3, 3, 3], [P, P, P, P, P]),
+        "repeated_mixed": ([3, 3, 3, 8, 8], [P, P, Q, Q, Q]),
+        "inf_input": ([9, 2, 1, 4], [None, P, None, Q]),
+        "all_inf": ([9, 2], [None, None]),
+        "full256": ([top, (1 << 255) + 12345, top - 1], [G, P, Q]),
+        "topbit_lowbit": ([1 << 255, 1, 1 << 254, 2], [G, P, Q, G]),
+        "small_scalars": (list(range(40)), pyec.chain_points(cv, 40, 3, 5)),
+        "same_scalar_many_points": ([0xABCDEF] * 64, pyec.chain_points(cv, 64, 9, 11)),
+        "neg_pairs_same_bucket": ([77] * 6, [P, Q, cv.neg(P), cv.neg(Q), P, cv.neg(P)]),
+    }
+    for name, (ks, pts) in sets.items():
+        want = cv.affine_to_bytes(cv.msm(ks, pts))
+        Pb = np.frombuffer(cv.points_to_bytes(pts), dtype=np.uint64).copy()
+        S = np.frombuffer(b"".join(cv.scalar_std_bytes(k) for k in ks), dtype=np.uint64).copy()
+        got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", S, Pb)
+        assert got.tobytes() == want, name
+        assert cpu_affine(curve, S, Pb).tobytes() == want, name  # and the oracle agrees with Python
+        if all(k < cv.r for k in ks):
+            Sm = np.frombuffer(b"".join(cv.scalar_mont_bytes(k) for k in ks), dtype=np.uint64).copy()
+            got = zk.call_reference_symbol(f"{curve}_G1_jac_MSM_mont_coeff_affine_out", Sm, Pb)
+            assert got.tobytes() == want, name + " (mont)"
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_window_widths_and_long_runs(zk, curve):
+    """every window width through the *_variable symbol; few distinct scalars => runs far longer than a chunk."""
+    L = refs.CURVE_LIMBS[curve]
+    n = 3000
+    pts = refs.chain_points(curve, n)
+    sc = refs.random_scalars(curve, n, seed=5, reduce=False)
+    want = cpu_affine(curve, sc, pts)
+    for c in (1, 2, 3, 5, 8, 9, 12, 16, 17):
+        out = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_proj_out_variable", sc, pts, window_size=c)
+        assert to_affine_cpu(curve, "proj", out).tobytes() == want.tobytes(), c
+    few = sc[:3]
+    sc2 = np.ascontiguousarray(few[np.arange(n) % 3])
+    want2 = cpu_affine(curve, sc2, pts)
+    for c in (4, 11):
+        out = zk.call_reference_symbol(f"{curve}_G1_jac_MSM_std_coeff_jac_out_variable", sc2, pts, window_size=c)
+        assert to_affine_cpu(curve, "jac", out).tobytes() == want2.tobytes(), c
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_short_scalars_expo_nlimbs(zk, curve):
+    L = refs.CURVE_LIMBS[curve]
+    n = 200
+    pts = refs.chain_points(curve, n)
+    lib, pre = cpu_lib()
+    for nl in (1, 2, 3):
+        sc = refs.random_scalars(curve, n, seed=nl, reduce=False)[:, :nl].copy()
+        want = refs.call_msm(lib, f"{pre}{curve}_G1_proj_MSM_std_coeff_affine_out", sc.ravel(), pts.ravel(), 2 * L, n=n, nlimbs=nl)
+        got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts, npoints=n, expo_nlimbs=nl)
+        assert got.tobytes() == want.tobytes(), nl
+
+
+@pytest.mark.parametrize("v", GOLDEN, ids=lambda g: f"{g['curve']}-{g['n']}-{g['form']}")
+def test_golden_vectors(zk, v):
+    """committed fixtures generated from the unmodified reference C (tests/golden/make_golden.py);
+    includes BASELINE configs[0]: BN254 2^16."""
+    curve, n, form = v["curve"], v["n"], v["form"]
+    pts = refs.chain_points(curve, n)
+    sc = refs.random_scalars(curve, n, seed=v["seed"], reduce=(form == "mont"))
+    got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_{form}_coeff_affine_out", sc, pts, npoints=n)
+    assert got.tobytes().hex() == v["affine_hex"]
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_batch_and_device_entry(zk, curve):
+    import torch
+    L = refs.CURVE_LIMBS[curve]
+    n, nmsm = 1 << 12, 5
+    pts = refs.chain_points(curve, n)
+    sc = np.stack([refs.random_scalars(curve, n, seed=50 + i) for i in range(nmsm)])
+    single = np.stack([zk.msm(curve, sc[i], pts, mont=True, out="affine") for i in range(nmsm)])
+    batch = zk.msm_batch(curve, sc, pts, mont=True, out="affine")
+    assert batch.tobytes() == single.tobytes()
+    for i in range(nmsm):
+        assert single[i].tobytes() == cpu_affine(curve, sc[i], pts, "mont").tobytes()
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    d_pts = torch.from_numpy(pts.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    dev = zk.msm_device(curve, d_sc.data_ptr(), d_pts.data_ptr(), n, nmsm=nmsm, mont=True, out="affine")
+    assert dev.tobytes() == single.tobytes()
+    st = zk.last_stats()
+    assert st["insertions"] == nmsm * n * st["nwindows"] and st["phase_ms"]["accumulate"] > 0
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_sharded_partials_combine(zk, curve):
+    """contiguous shards -> partial proj/xyzz results -> zkb200_sum_points == unsharded answer (multi-GPU combine, K8)."""
+    n = 6000
+    pts = refs.chain_points(curve, n)
+    sc = refs.random_scalars(curve, n, seed=77)
+    want = cpu_affine(curve, sc, pts, "mont")
+    for rep in ("proj", "jac", "xyzz"):
+        parts = []
+        for k in range(4):
+            lo, hi = n * k // 4, n * (k + 1) // 4
+            parts.append(zk.msm(curve, sc[lo:hi], pts[lo:hi], mont=True, out=rep))
+        got = zk.sum_points(curve, np.stack(parts), in_repr=rep, out="affine")
+        assert got.tobytes() == want.tobytes(), rep
+    # a partial that is infinity, and opposite partials
+    cv = pyec.CURVES[curve]
+    inf = zk.msm(curve, np.zeros((2, 4), np.uint64), pts[:2], mont=False, out="proj")
+    assert zk.sum_points(curve, np.stack([inf, inf]), "proj", "affine").tobytes() == b"\xff" * cv.affine_bytes
+
+
+@pytest.mark.parametrize("curve,logn", [("bn128", 18), ("bls12_381", 17)])
+def test_mid_size_vs_threaded_reference(zk, curve, logn):
+    n = 1 << logn
+    pts = refs.chain_points(curve, n)
+    sc = refs.random_scalars(curve, n, seed=logn)
+    want = refs.ref_msm_threads(curve, sc, pts, mont=True, nthreads=os.cpu_count() or 4)
+    got = zk.msm(curve, sc, pts, mont=True, out="affine")
+    assert got.tobytes() == want.tobytes()
+
+
+def test_full_size_properties_bls12_381_2_20(zk):
+    """BASELINE configs[1] size (BLS12-381, 2^20): size-independent properties instead of a CPU run.
+    (1) split: MSM(all) == MSM(first half) + MSM(second half);  (2) linearity in the scalars:
+    MSM(k) + MSM(k') == MSM(k + k' mod 2^256 as integers when no overflow)."""
+    curve = "bls12_381"
+    n = 1 << 20
+    pts = refs.chain_points(curve, n)
+    sc = refs.random_scalars(curve, n, seed=2020)          # < 2^253
+    whole = zk.msm(curve, sc, pts, mont=False, out="affine")
+    h = n // 2
+    a = zk.msm(curve, sc[:h], pts[:h], mont=False, out="proj")
+    b = zk.msm(curve, sc[h:], pts[h:], mont=False, out="proj")
+    assert zk.sum_points(curve, np.stack([a, b]), "proj", "affine").tobytes() == whole.tobytes()
+    sc2 = refs.random_scalars(curve, n, seed=2021)
+    # limb-wise big-int addition with carries (values < 2^253, so the sum fits in 256 bits)
+    s = np.zeros_like(sc)
+    carry = np.zeros(n, dtype=np.uint64)
+    for j in range(4):
+        t = sc[:, j] + sc2[:, j]
+        c1 = (t < sc[:, j]).astype(np.uint64)
+        t2 = t + carry
+        c2 = (t2 < t).astype(np.uint64)
+        s[:, j] = t2
+        carry = c1 + c2
+    assert not carry.any()
+    x = zk.msm(curve, sc, pts, mont=False, out="jac")
+    y = zk.msm(curve, sc2, pts, mont=False, out="jac")
+    z = zk.msm(curve, s, pts, mont=False, out="affine")
+    assert zk.sum_points(curve, np.stack([x, y]), "jac", "affine").tobytes() == z.tobytes()
+    # and a 2^16 prefix of the same inputs against the CPU reference
+    m = 1 << 16
+    assert zk.msm(curve, sc[:m], pts[:m], mont=False).tobytes() == cpu_affine(curve, sc[:m], pts[:m]).tobytes()
+
+
+def test_imad_probe_runs(zk):
+    v = zk.imad_peak(0, 200)
+    assert v > 1e11

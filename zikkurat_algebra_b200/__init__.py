@@ -1,0 +1,198 @@
+"""zikkurat_algebra_b200 -- B200 (sm_100a) G1 multi-scalar multiplication for BN254 / BLS12-381.
+
+Host-side mirror (Python, ctypes) of the reference's MSM interface over the C-ABI shared library
+``lib/libzkmsm_b200.so`` (include/zk_msm_b200.h).  Mirrors the generated Haskell bindings
+
+    ZK.Algebra.Curves.<Curve>.G1.Proj.msm / msmStd      lib/src/ZK/Algebra/Curves/BN128/G1/Proj.hs:228-263
+    ZK.Algebra.Curves.<Curve>.G1.Affine.msm / msmStd    lib/src/ZK/Algebra/Curves/BN128/G1/Affine.hs:144-149
+
+over flat little-endian uint64 arrays (the FlatArray layout of lib/src/ZK/Algebra/Class/Flat.hs:81-90).
+There is no CPU implementation in this package: importing works anywhere (so that the library's exported
+symbols can be inspected), every compute call needs a CUDA device and aborts without one.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+__all__ = [
+    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "call_reference_symbol",
+    "last_stats", "imad_peak", "set_device", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libzkmsm_b200.so")
+
+CURVES = {"bn128": dict(id=0, nlimbs_p=4), "bls12_381": dict(id=1, nlimbs_p=6)}
+OUT_PROJ, OUT_JAC, OUT_AFFINE, OUT_XYZZ = 0, 1, 2, 3
+_OUT = {"proj": OUT_PROJ, "jac": OUT_JAC, "affine": OUT_AFFINE, "xyzz": OUT_XYZZ}
+_OUT_COORDS = {OUT_PROJ: 3, OUT_JAC: 3, OUT_AFFINE: 2, OUT_XYZZ: 4}
+HOST, DEVICE = 0, 1
+
+REFERENCE_SYMBOLS = [
+    f"{c}_G1_{r}_MSM_{f}_coeff_{o}_out"
+    for c in ("bn128", "bls12_381")
+    for r in ("proj", "jac")
+    for f in ("std", "mont")
+    for o in (r, "affine")
+] + [f"{c}_G1_{r}_MSM_std_coeff_{r}_out_variable" for c in ("bn128", "bls12_381") for r in ("proj", "jac")]
+EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
+                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count"]
+
+_U64P = ctypes.POINTER(ctypes.c_uint64)
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The C-ABI library.  Fails loudly when it has not been built (python zikkurat_algebra_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: build it with `python zikkurat_algebra_b200/build.py` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        L = ctypes.CDLL(_LIB_PATH)
+        L.zkb200_msm.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _U64P]
+        L.zkb200_msm.restype = None
+        L.zkb200_sum_points.argtypes = [ctypes.c_int, ctypes.c_int, _U64P, ctypes.c_int, ctypes.c_int, _U64P]
+        L.zkb200_sum_points.restype = None
+        L.zkb200_set_device.argtypes = [ctypes.c_int]
+        L.zkb200_set_device.restype = None
+        L.zkb200_last_stats.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int),
+                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_longlong)]
+        L.zkb200_last_stats.restype = None
+        L.zkb200_imad_peak.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.zkb200_imad_peak.restype = ctypes.c_double
+        L.zkb200_version.restype = ctypes.c_char_p
+        L.zkb200_gen_chain.argtypes = [ctypes.c_int, ctypes.c_ulonglong, ctypes.c_long, _U64P, _U64P, ctypes.c_void_p, ctypes.c_int]
+        L.zkb200_gen_chain.restype = None
+        L.zkb200_launch_count.restype = ctypes.c_longlong
+        for name in REFERENCE_SYMBOLS:
+            f = getattr(L, name)
+            f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P, ctypes.c_int] + ([ctypes.c_int] if name.endswith("_variable") else [])
+            f.restype = None
+        _lib = L
+    return _lib
+
+
+def _as_u64(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_U64P)
+
+
+def set_device(device: int) -> None:
+    lib().zkb200_set_device(int(device))
+
+
+def call_reference_symbol(name: str, scalars: np.ndarray, points: np.ndarray, npoints: Optional[int] = None,
+                          expo_nlimbs: int = 4, window_size: Optional[int] = None) -> np.ndarray:
+    """Call one of the reference-named entry points exactly as the reference's FFI would
+    (void f(int npoints, const uint64_t* expos, const uint64_t* grps, uint64_t* tgt, int expo_nlimbs))."""
+    curve = "bls12_381" if name.startswith("bls12_381") else "bn128"
+    L = CURVES[curve]["nlimbs_p"]
+    coords = 2 if "affine_out" in name else 3
+    s = _as_u64(scalars).ravel()
+    p = _as_u64(points).ravel()
+    n = s.size // expo_nlimbs if npoints is None else npoints
+    out = np.zeros(coords * L, dtype=np.uint64)
+    s_ = s if s.size else np.zeros(1, np.uint64)
+    p_ = p if p.size else np.zeros(1, np.uint64)
+    f = getattr(lib(), name)
+    if name.endswith("_variable"):
+        f(n, _ptr(s_), _ptr(p_), _ptr(out), expo_nlimbs, int(window_size or 0))
+    else:
+        f(n, _ptr(s_), _ptr(p_), _ptr(out), expo_nlimbs)
+    return out
+
+
+def msm_batch(curve: str, scalars: np.ndarray, points: np.ndarray, mont: bool = True, out: str = "affine",
+              window: int = 0, expo_nlimbs: int = 4) -> np.ndarray:
+    """nmsm independent MSMs over one shared point array.  scalars: (nmsm, n, expo_nlimbs) uint64,
+    points: (n, 2L) uint64 (host arrays).  Returns (nmsm, coords*L) uint64."""
+    cv = CURVES[curve]
+    s = _as_u64(scalars)
+    p = _as_u64(points)
+    nmsm, n = s.shape[0], s.shape[1]
+    mode = _OUT[out]
+    res = np.zeros((nmsm, _OUT_COORDS[mode] * cv["nlimbs_p"]), dtype=np.uint64)
+    lib().zkb200_msm(cv["id"], nmsm, n, s.ctypes.data if s.size else None, HOST, p.ctypes.data if p.size else None, HOST,
+                     expo_nlimbs, int(mont), mode, window, _ptr(res))
+    return res
+
+
+def msm(curve: str, scalars: np.ndarray, points: np.ndarray, mont: bool = True, out: str = "affine",
+        window: int = 0, expo_nlimbs: int = 4) -> np.ndarray:
+    """sum_i k_i * P_i.  `mont=True` = Curve.msm (Montgomery Fr coefficients), `mont=False` = msmStd."""
+    s = _as_u64(scalars).reshape(1, -1, expo_nlimbs)
+    return msm_batch(curve, s, points, mont=mont, out=out, window=window, expo_nlimbs=expo_nlimbs)[0]
+
+
+def msm_std(curve: str, scalars: np.ndarray, points: np.ndarray, **kw) -> np.ndarray:
+    return msm(curve, scalars, points, mont=False, **kw)
+
+
+def msm_device(curve: str, scalars_ptr: int, points_ptr: int, npoints: int, nmsm: int = 1, mont: bool = True,
+               out: str = "affine", window: int = 0, expo_nlimbs: int = 4) -> np.ndarray:
+    """Same computation with inputs already resident in the current device's memory (raw device pointers,
+    e.g. torch.Tensor.data_ptr()); only the result crosses PCIe."""
+    cv = CURVES[curve]
+    mode = _OUT[out]
+    res = np.zeros((nmsm, _OUT_COORDS[mode] * cv["nlimbs_p"]), dtype=np.uint64)
+    lib().zkb200_msm(cv["id"], nmsm, npoints, scalars_ptr, DEVICE, points_ptr, DEVICE, expo_nlimbs, int(mont), mode,
+                     window, _ptr(res))
+    return res
+
+
+def sum_points(curve: str, pts: np.ndarray, in_repr: str = "proj", out: str = "affine") -> np.ndarray:
+    """Sum of k group elements in a reference representation (the multi-GPU combine of partial MSMs)."""
+    cv = CURVES[curve]
+    a = _as_u64(pts)
+    k = a.shape[0] if a.ndim == 2 else 1
+    mode = _OUT[out]
+    res = np.zeros(_OUT_COORDS[mode] * cv["nlimbs_p"], dtype=np.uint64)
+    lib().zkb200_sum_points(cv["id"], k, _ptr(a.ravel()), _OUT[in_repr], mode, _ptr(res))
+    return res
+
+
+def gen_chain(curve: str, n: int, p0: np.ndarray, d: np.ndarray, start: int = 0, device_ptr: Optional[int] = None) -> Optional[np.ndarray]:
+    """Synthetic points out[i] = P0 + (start+i)*D (affine Montgomery records), computed on the GPU.
+    With `device_ptr` the points are written to that device buffer and None is returned."""
+    cv = CURVES[curve]
+    p0 = _as_u64(p0).ravel()
+    d = _as_u64(d).ravel()
+    if device_ptr is not None:
+        lib().zkb200_gen_chain(cv["id"], start, n, _ptr(p0), _ptr(d), device_ptr, DEVICE)
+        return None
+    out = np.zeros((n, 2 * cv["nlimbs_p"]), dtype=np.uint64)
+    lib().zkb200_gen_chain(cv["id"], start, n, _ptr(p0), _ptr(d), out.ctypes.data, HOST)
+    return out
+
+
+def launch_count() -> int:
+    return int(lib().zkb200_launch_count())
+
+
+def last_stats() -> dict:
+    ms = (ctypes.c_float * 9)()
+    c, w, ins = ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+    lib().zkb200_last_stats(ms, ctypes.byref(c), ctypes.byref(w), ctypes.byref(ins))
+    names = ["h2d_scalars", "recode", "sort", "wait_points", "accumulate", "fixup", "reduce", "tail_d2h", "total"]
+    return {"phase_ms": dict(zip(names, [float(x) for x in ms])), "window": c.value, "nwindows": w.value,
+            "insertions": ins.value}
+
+
+def imad_peak(kind: int = 0, iters: int = 2000) -> float:
+    """Measured 32x32-bit products per second of the whole GPU (see zkb200_imad_peak)."""
+    return float(lib().zkb200_imad_peak(kind, iters))

@@ -1,0 +1,229 @@
+// Montgomery prime-field arithmetic on 32-bit limbs, one field element per thread, fully unrolled.
+//
+// Replaces (value-for-value; results are canonical < p exactly like the reference's):
+//   bn128_Fp_mont_mul/_sqr        lib/cbits/curves/fields/mont/bn128_Fp_mont.c:177-199
+//     = bigint256_mul             lib/cbits/bigint/bigint256.c:267-356   (schoolbook product)
+//     + REDC_unsafe               lib/cbits/curves/fields/mont/bn128_Fp_mont.c:140-169
+//   bn128_Fp_mont_add/_sub/_neg   lib/cbits/curves/fields/mont/bn128_Fp_mont.c:44-109
+//   bn128_Fr_mont_to_std          lib/cbits/curves/fields/mont/bn128_Fr_mont.c:330-335
+// and the bls12_381 twins (6x64-bit limbs there, 12x32-bit limbs here).
+//
+// Multiplication is the interleaved (CIOS-style) Montgomery product split into an "even" and an
+// "odd" accumulator so that every 32x32->64 product lands on an aligned (lo,hi) register pair:
+//   T = E + O * 2^32,  E holds limb positions 0..L-1, O holds positions 1..L.
+// A row  T += a * b_i  is then two independent carry chains of L/2 products each
+// (mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32 with carry), and the /2^32 of each Montgomery
+// step swaps the roles of the two accumulators instead of moving registers.
+// Product count per multiplication: L*L (a*b) + L*L (m*p) + L (m) = 2L^2 + L  (136 | 300).
+#pragma once
+#include "hd.cuh"
+
+namespace zk {
+
+template <class P>
+struct Fe {
+  static constexpr int L = P::L;
+  uint32_t l[P::L];
+};
+
+// acc[0..L) (+)= a[s], a[s+2], ... times b, one carry chain; CARRY_IN continues a previous chain.
+// After the call the carry flag holds the carry out of acc[L-1].
+template <int L, bool CARRY_IN>
+ZK_HD void cmad_row(uint32_t* acc, const uint32_t* a, uint32_t b) {
+#pragma unroll
+  for (int j = 0; j < L; j += 2) {
+    acc[j] = (j == 0 && !CARRY_IN) ? mad_lo_cc(a[j], b, acc[j]) : madc_lo_cc(a[j], b, acc[j]);
+    acc[j + 1] = madc_hi_cc(a[j], b, acc[j + 1]);
+  }
+}
+
+template <class P, int S>
+struct ModRow {  // the constant row p[S], p[S+2], ... as an indexable object
+  ZK_HD constexpr uint32_t operator[](int j) const { return P::mod(j + S); }
+};
+
+template <int L, class Row>
+ZK_HD void cmad_row_const(uint32_t* acc, Row p, uint32_t m) {
+#pragma unroll
+  for (int j = 0; j < L; j += 2) {
+    acc[j] = (j == 0) ? mad_lo_cc(p[j], m, acc[j]) : madc_lo_cc(p[j], m, acc[j]);
+    acc[j + 1] = madc_hi_cc(p[j], m, acc[j + 1]);
+  }
+}
+
+// r = r - p if r >= p   (r < 2p on entry)
+template <class P>
+ZK_HD void final_sub(uint32_t* r) {
+  constexpr int L = P::L;
+  uint32_t t[L];
+  t[0] = sub_cc(r[0], P::mod(0));
+#pragma unroll
+  for (int i = 1; i < L; i++) t[i] = subc_cc(r[i], P::mod(i));
+  uint32_t borrow = subc(0u, 0u);  // 0xffffffff if r < p
+#pragma unroll
+  for (int i = 0; i < L; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+// Montgomery product, inputs canonical, output canonical.
+template <class P>
+ZK_HD void mont_mul_limbs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int L = P::L;
+  static_assert(L % 2 == 0, "even limb count expected");
+  uint32_t A[L], B[L];  // the two accumulators; roles alternate every row
+  // ---- row 0: plain products, no accumulate ----
+#pragma unroll
+  for (int j = 0; j < L; j += 2) {
+    A[j] = mul_lo(a[j], b[0]);
+    A[j + 1] = mul_hi(a[j], b[0]);
+    B[j] = mul_lo(a[j + 1], b[0]);
+    B[j + 1] = mul_hi(a[j + 1], b[0]);
+  }
+  {
+    uint32_t m = mul_lo(A[0], P::INV);
+    cmad_row_const<L>(B, ModRow<P, 1>(), m);  // carry out is provably 0
+    cmad_row_const<L>(A, ModRow<P, 0>(), m);
+    B[L - 1] = addc(B[L - 1], 0u);
+  }
+  // ---- rows 1..L-1 ----
+#pragma unroll
+  for (int i = 1; i < L; i++) {
+    uint32_t* E = (i & 1) ? B : A;  // becomes the even accumulator of this row (was odd)
+    uint32_t* O = (i & 1) ? A : B;  // old even accumulator; O[0] == 0, shifted down two limbs in place
+    E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 0; j < L - 2; j += 2) {
+      O[j] = madc_lo_cc(a[j + 1], b[i], O[j + 2]);
+      O[j + 1] = madc_hi_cc(a[j + 1], b[i], O[j + 3]);
+    }
+    O[L - 2] = madc_lo_cc(a[L - 1], b[i], 0u);
+    O[L - 1] = madc_hi(a[L - 1], b[i], 0u);
+    cmad_row<L, false>(E, a, b[i]);
+    O[L - 1] = addc(O[L - 1], 0u);
+    uint32_t m = mul_lo(E[0], P::INV);
+    cmad_row_const<L>(O, ModRow<P, 1>(), m);
+    cmad_row_const<L>(E, ModRow<P, 0>(), m);
+    O[L - 1] = addc(O[L - 1], 0u);
+  }
+  // ---- combine: result = E / 2^32 + O ----
+  uint32_t* E = ((L - 1) & 1) ? B : A;
+  uint32_t* O = ((L - 1) & 1) ? A : B;
+  r[0] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 1; k < L - 1; k++) r[k] = addc_cc(E[k + 1], O[k]);
+  r[L - 1] = addc(O[L - 1], 0u);
+  final_sub<P>(r);
+}
+
+template <class P>
+ZK_HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  mont_mul_limbs<P>(r.l, a.l, b.l);
+  return r;
+}
+template <class P>
+ZK_HD Fe<P> fe_sqr(const Fe<P>& a) {
+  return fe_mul<P>(a, a);
+}
+
+template <class P>
+ZK_HD Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int L = P::L;
+  Fe<P> r;
+  r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < L - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+  r.l[L - 1] = addc(a.l[L - 1], b.l[L - 1]);  // p < 2^(32L-1): no carry out
+  final_sub<P>(r.l);
+  return r;
+}
+
+template <class P>
+ZK_HD Fe<P> fe_sub(const Fe<P>& a, const Fe<P>& b) {
+  constexpr int L = P::L;
+  Fe<P> r;
+  r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < L; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+  uint32_t borrow = subc(0u, 0u);  // all-ones when a < b
+  r.l[0] = add_cc(r.l[0], P::mod(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < L - 1; i++) r.l[i] = addc_cc(r.l[i], P::mod(i) & borrow);
+  r.l[L - 1] = addc(r.l[L - 1], P::mod(L - 1) & borrow);
+  return r;
+}
+
+template <class P>
+ZK_HD bool fe_is_zero(const Fe<P>& a) {
+  uint32_t o = a.l[0];
+#pragma unroll
+  for (int i = 1; i < P::L; i++) o |= a.l[i];
+  return o == 0;
+}
+
+template <class P>
+ZK_HD Fe<P> fe_neg(const Fe<P>& a) {  // 0 -> 0, else p - a
+  constexpr int L = P::L;
+  Fe<P> r;
+  uint32_t nz = fe_is_zero<P>(a) ? 0u : 0xffffffffu;
+  r.l[0] = sub_cc(P::mod(0) & nz, a.l[0]);
+#pragma unroll
+  for (int i = 1; i < L - 1; i++) r.l[i] = subc_cc(P::mod(i) & nz, a.l[i]);
+  r.l[L - 1] = subc(P::mod(L - 1) & nz, a.l[L - 1]);
+  return r;
+}
+
+template <class P>
+ZK_HD Fe<P> fe_dbl(const Fe<P>& a) {
+  return fe_add<P>(a, a);
+}
+
+template <class P>
+ZK_HD Fe<P> fe_zero() {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < P::L; i++) r.l[i] = 0;
+  return r;
+}
+template <class P>
+ZK_HD Fe<P> fe_one() {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < P::L; i++) r.l[i] = P::one(i);
+  return r;
+}
+template <class P>
+ZK_HD bool fe_eq(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < P::L; i++) o |= a.l[i] ^ b.l[i];
+  return o == 0;
+}
+
+// Montgomery -> standard representation: one REDC of (a, 0), i.e. a * 1 * R^-1.
+template <class P>
+ZK_HD Fe<P> fe_from_mont(const Fe<P>& a) {
+  Fe<P> one_std = fe_zero<P>();
+  one_std.l[0] = 1;
+  return fe_mul<P>(a, one_std);
+}
+
+// a^(p-2) by square-and-multiply over the constant exponent (used once per MSM for to_affine).
+template <class P>
+ZK_HD Fe<P> fe_inv(const Fe<P>& a) {
+  constexpr int L = P::L;
+  Fe<P> acc = fe_one<P>();
+  bool started = false;
+  for (int i = 32 * L - 1; i >= 0; i--) {
+    // exponent p - 2: p is odd and p mod 2^32 >= 2 for both primes, so only limb 0 changes
+    uint32_t w = P::mod(i >> 5) - ((i >> 5) == 0 ? 2u : 0u);
+    uint32_t bit = (w >> (i & 31)) & 1u;
+    if (started) acc = fe_sqr<P>(acc);
+    if (bit) {
+      acc = started ? fe_mul<P>(acc, a) : a;
+      started = true;
+    }
+  }
+  return acc;
+}
+
+}  // namespace zk

@@ -1,0 +1,149 @@
+// Kernels K1/K2 (recode) and K4 (bucket accumulation + head fix-up) with their launchers.
+// See msm_common.cuh for vocabulary.  Reference loops replaced:
+//   lib/cbits/curves/g1/proj/bn128_G1_proj.c:520-561 (digit extraction + bucket accumulation)
+//   lib/cbits/curves/g1/proj/bn128_G1_proj.c:629-643 (Fr Montgomery -> standard conversion)
+#pragma once
+#include "msm_common.cuh"
+
+namespace zk {
+
+// ---- K1 + K2: Fr Montgomery -> standard (optional) and signed-digit recoding ---------------------------
+// scalars: nmsm*n records of `nl64` 64-bit limbs.  Output pairs are segment-major.
+template <class C>
+__global__ void __launch_bounds__(256)
+k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int mont, int nbits, int c, int W,
+         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * (size_t)nmsm) return;
+  size_t msm = gid / n, i = gid - msm * n;
+  Fe<typename C::Fr> k;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(scalars + gid * (size_t)nl64);
+  if (nl64 == 4) {
+    const uint4* q = reinterpret_cast<const uint4*>(src);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    k.l[0] = a.x; k.l[1] = a.y; k.l[2] = a.z; k.l[3] = a.w;
+    k.l[4] = b.x; k.l[5] = b.y; k.l[6] = b.z; k.l[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) k.l[j] = (j < 2 * nl64) ? src[j] : 0u;
+  }
+  if (mont) k = fe_from_mont<typename C::Fr>(k);
+  uint32_t carry = 0;
+  size_t seg0 = msm * (size_t)W;
+  for (int w = 0; w < W; w++) {
+    uint32_t key, neg;
+    recode_digit(k.l, nbits, c, w, carry, key, neg);
+    size_t o = (seg0 + w) * n + i;
+    keys[o] = key;
+    vals[o] = (uint32_t)i | (neg << 31);
+  }
+}
+
+// ---- K4: bucket accumulation ---------------------------------------------------------------------------
+// Every thread owns `chunk` consecutive SORTED pairs of one segment and folds each run of equal keys
+// into one XYZZ sum (xyzz_madd = the IMAD-bound inner operation).  Runs that begin inside the chunk
+// are complete from this thread's point of view and are stored straight to their bucket (unique
+// writer); the chunk's first run may continue a run of the previous chunk and goes to heads[t]
+// instead, to be folded in by k_fixup.  Work per thread is exactly `chunk` insertions whatever the
+// scalar distribution, so there is no bucket-size imbalance.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+             const uint32_t* __restrict__ points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
+             uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets,
+             XyzzMem<typename C::Fp>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
+  using P = typename C::Fp;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nseg * chunks_per_seg) return;
+  uint32_t seg = (uint32_t)(t / chunks_per_seg);
+  uint32_t j = (uint32_t)(t - (size_t)seg * chunks_per_seg);
+  size_t start = (size_t)j * chunk;
+  size_t end = start + chunk < n ? start + chunk : n;
+  const uint32_t* kp = keys + (size_t)seg * n;
+  const uint32_t* vp = vals + (size_t)seg * n;
+  XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
+
+  Xyzz<P> acc = xyzz_inf<P>();
+  uint32_t cur = 0;      // key of the open run (0 = none)
+  bool head_open = true;  // the open run is the chunk's first one
+  uint32_t head_key = 0;
+  for (size_t e = start; e < end; e++) {
+    uint32_t key = kp[e];
+    if (key == 0) continue;  // digit 0: no insertion (these sort to the front of the segment)
+    uint32_t v = vp[e];
+    Affine<P> pt = load_affine<P>(points, v & 0x7fffffffu);
+    bool inf = affine_is_inf<P>(pt);
+    Fe<P> ny = fe_neg<P>(pt.y);
+    if (v >> 31) pt.y = ny;
+    if (key != cur) {
+      if (cur != 0) {
+        if (head_open) { store_xyzz<P>(heads + t, acc); head_key = cur; head_open = false; }
+        else store_xyzz<P>(bseg + (cur - 1), acc);
+      }
+      cur = key;
+      acc = inf ? xyzz_inf<P>() : xyzz_from_affine<P>(pt);
+    } else if (!inf) {
+      xyzz_madd<P>(acc, pt);
+    }
+  }
+  if (cur != 0) {
+    if (head_open) { store_xyzz<P>(heads + t, acc); head_key = cur; }
+    else store_xyzz<P>(bseg + (cur - 1), acc);
+  }
+  head_keys[t] = head_key;
+}
+
+// Fold the per-chunk head sums into their buckets.  Consecutive chunks of a segment whose head runs
+// carry the same key form a group; the first thread of a group adds the whole group (sequentially).
+template <class C>
+__global__ void __launch_bounds__(128)
+k_fixup(const uint32_t* __restrict__ head_keys, const XyzzMem<typename C::Fp>* __restrict__ heads,
+        int nseg, uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets) {
+  using P = typename C::Fp;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nseg * chunks_per_seg) return;
+  uint32_t seg = (uint32_t)(t / chunks_per_seg);
+  uint32_t j = (uint32_t)(t - (size_t)seg * chunks_per_seg);
+  uint32_t key = head_keys[t];
+  if (key == 0) return;
+  if (j > 0 && head_keys[t - 1] == key) return;  // not the group leader
+  XyzzMem<P>* b = buckets + (size_t)seg * NB + (key - 1);
+  Xyzz<P> acc = load_xyzz<P>(b);
+  size_t u = t;
+  uint32_t jj = j;
+  do {
+    acc = xyzz_add<P>(acc, load_xyzz<P>(heads + u));
+    u++; jj++;
+  } while (jj < chunks_per_seg && head_keys[u] == key);
+  store_xyzz<P>(b, acc);
+}
+
+
+template <class C>
+void launch_recode(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int nbits, int c, int W,
+                   uint32_t* keys, uint32_t* vals) {
+  size_t tot = (size_t)nmsm * n;
+  k_recode<C><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(scalars, nl64, n, nmsm, mont, nbits, c, W, keys, vals);
+}
+template <class C>
+void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int nseg,
+                       int chunk, uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets,
+                       XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
+  size_t nthreads = (size_t)nseg * chunks_per_seg;
+  k_accumulate<C><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg, NB,
+                                                                    buckets, heads, head_keys);
+}
+template <class C>
+void launch_fixup(cudaStream_t s, const uint32_t* head_keys, const XyzzMem<typename C::Fp>* heads, int nseg,
+                  uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets) {
+  size_t nthreads = (size_t)nseg * chunks_per_seg;
+  k_fixup<C><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(head_keys, heads, nseg, chunks_per_seg, NB, buckets);
+}
+
+#define ZK_INSTANTIATE_ACC(C)                                                                                              \
+  template void launch_recode<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, int, uint32_t*, uint32_t*); \
+  template void launch_accumulate<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,     \
+                                     uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);                      \
+  template void launch_fixup<C>(cudaStream_t, const uint32_t*, const XyzzMem<C::Fp>*, int, uint32_t, uint32_t, XyzzMem<C::Fp>*);
+
+}  // namespace zk

@@ -1,0 +1,189 @@
+// Kernels K5 (bucket reduction by levels), K6/K7 (window combination, output conversion) and K8
+// (sum of partial results) with their launchers.  Reference loops replaced:
+//   lib/cbits/curves/g1/proj/bn128_G1_proj.c:565-582 (running sums, Horner over windows)
+//   lib/cbits/curves/g1/proj/bn128_G1_proj.c:132-144 (to_affine)
+#pragma once
+#include "msm_common.cuh"
+
+namespace zk {
+
+// Out-of-line group operations for the latency-bound kernels (reduce_next, tail, sum): keeps their code
+// size and compile time down; the throughput kernels (accumulate, reduce_first) inline everything.
+template <class P>
+__device__ __noinline__ void xyzz_add_nc(Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add<P>(a, b); }
+template <class P>
+__device__ __noinline__ void xyzz_dbl_nc(Xyzz<P>& a) { a = xyzz_dbl<P>(a); }
+
+// ---- K5: bucket reduction  sum_b (b+1) * B[b]  by levels ------------------------------------------------
+// Invariant after every level:  R_seg = sum_t ( U[t] + M * t * V[t] ),  t = 0..S-1.
+// Level 1 reads the buckets (U = V = B, M = 1, weights t+1) with the classic running sum over m buckets.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_reduce_first(const XyzzMem<typename C::Fp>* __restrict__ buckets, size_t total_out, int log_m,
+               XyzzMem<typename C::Fp>* __restrict__ U, XyzzMem<typename C::Fp>* __restrict__ V) {
+  using P = typename C::Fp;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_out) return;
+  const XyzzMem<P>* b = buckets + (t << log_m);
+  Xyzz<P> run = xyzz_inf<P>(), acc = xyzz_inf<P>();
+  for (int i = (1 << log_m) - 1; i >= 0; i--) {
+    run = xyzz_add<P>(run, load_xyzz<P>(b + i));
+    acc = xyzz_add<P>(acc, run);
+  }
+  store_xyzz<P>(U + t, acc);
+  store_xyzz<P>(V + t, run);
+}
+// Next levels: groups of m entries (t = g*m + i):
+//   U'[g] = sum_i U[t] + M * sum_i i*V[t],   V'[g] = sum_i V[t],   M' = M*m,   M = 2^log_M.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typename C::Fp>* __restrict__ Vin,
+              size_t total_out, int log_m, int log_M, XyzzMem<typename C::Fp>* __restrict__ Uout,
+              XyzzMem<typename C::Fp>* __restrict__ Vout) {
+  using P = typename C::Fp;
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_out) return;
+  const XyzzMem<P>* u = Uin + (g << log_m);
+  const XyzzMem<P>* v = Vin + (g << log_m);
+  Xyzz<P> run = xyzz_inf<P>(), acc = xyzz_inf<P>(), usum = xyzz_inf<P>();
+  for (int i = (1 << log_m) - 1; i >= 1; i--) {
+    xyzz_add_nc<P>(run, load_xyzz<P>(v + i));
+    xyzz_add_nc<P>(acc, run);
+    xyzz_add_nc<P>(usum, load_xyzz<P>(u + i));
+  }
+  xyzz_add_nc<P>(run, load_xyzz<P>(v));
+  xyzz_add_nc<P>(usum, load_xyzz<P>(u));
+  for (int d = 0; d < log_M; d++) xyzz_dbl_nc<P>(acc);
+  xyzz_add_nc<P>(usum, acc);
+  store_xyzz<P>(Uout + g, usum);
+  store_xyzz<P>(Vout + g, run);
+}
+
+// ---- K6 + K7: window combination (Horner) and output conversion ------------------------------------------
+
+template <class P>
+ZK_D void write_fe(uint32_t* dst, const Fe<P>& a) {
+#pragma unroll
+  for (int i = 0; i < P::L; i++) dst[i] = a.l[i];
+}
+template <class P>
+ZK_D Fe<P> read_fe(const uint32_t* src) {
+  Fe<P> a;
+#pragma unroll
+  for (int i = 0; i < P::L; i++) a.l[i] = src[i];
+  return a;
+}
+template <class P>
+ZK_D void write_result(uint32_t* o, const Xyzz<P>& acc, int mode) {
+  constexpr int L = P::L;
+  if (mode == OUT_AFFINE) {
+    Affine<P> a;
+    if (xyzz_to_affine<P>(acc, a)) { write_fe<P>(o, a.x); write_fe<P>(o + L, a.y); }
+    else { for (int i = 0; i < 2 * L; i++) o[i] = 0xffffffffu; }
+  } else if (mode == OUT_XYZZ) {
+    write_fe<P>(o, acc.X); write_fe<P>(o + L, acc.Y); write_fe<P>(o + 2 * L, acc.ZZ); write_fe<P>(o + 3 * L, acc.ZZZ);
+  } else {
+    Fe<P> X, Y, Z;
+    if (mode == OUT_PROJ) xyzz_to_proj<P>(acc, X, Y, Z); else xyzz_to_jac<P>(acc, X, Y, Z);
+    write_fe<P>(o, X); write_fe<P>(o + L, Y); write_fe<P>(o + 2 * L, Z);
+  }
+}
+// one thread per MSM of the batch; Rw[msm*W + w] = window sums; out record stride = 4L words
+template <class C>
+__global__ void k_tail(const XyzzMem<typename C::Fp>* __restrict__ Rw, int nmsm, int W, int c, int mode,
+                       uint32_t* __restrict__ out) {
+  using P = typename C::Fp;
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nmsm) return;
+  Xyzz<P> acc = xyzz_inf<P>();
+  if (W > 0) {
+    acc = load_xyzz<P>(Rw + (size_t)m * W + (W - 1));
+    for (int w = W - 2; w >= 0; w--) {
+      for (int d = 0; d < c; d++) xyzz_dbl_nc<P>(acc);
+      xyzz_add_nc<P>(acc, load_xyzz<P>(Rw + (size_t)m * W + w));
+    }
+  }
+  write_result<P>(out + (size_t)m * (4 * P::L), acc, mode);
+}
+
+// sum of k group elements given in one of the reference's representations (multi-GPU combine, K8)
+//   in_mode: OUT_PROJ / OUT_JAC / OUT_XYZZ (records of 3L / 3L / 4L words)
+template <class C>
+__global__ void k_sum_points(const uint32_t* __restrict__ in, int k, int in_mode, int out_mode, uint32_t* __restrict__ out) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int i = 0; i < k; i++) {
+    Xyzz<P> p;
+    if (in_mode == OUT_XYZZ) {
+      const uint32_t* s = in + (size_t)i * 4 * L;
+      p.X = read_fe<P>(s); p.Y = read_fe<P>(s + L); p.ZZ = read_fe<P>(s + 2 * L); p.ZZZ = read_fe<P>(s + 3 * L);
+    } else {
+      const uint32_t* s = in + (size_t)i * 3 * L;
+      Fe<P> X = read_fe<P>(s), Y = read_fe<P>(s + L), Z = read_fe<P>(s + 2 * L);
+      p = (in_mode == OUT_PROJ) ? xyzz_from_proj<P>(X, Y, Z) : xyzz_from_jac<P>(X, Y, Z);
+    }
+    xyzz_add_nc<P>(acc, p);
+  }
+  write_result<P>(out, acc, out_mode);
+}
+
+
+// Workload synthesis (not on the MSM path): out[i] = P0 + (start + i) * D as canonical affine points.
+// One thread per point: double-and-add of the index, one mixed add, one inversion.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_gen_chain(const uint32_t* __restrict__ p0d, unsigned long long start, size_t n, uint32_t* __restrict__ out) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<P> p0, d;
+  p0.x = read_fe<P>(p0d); p0.y = read_fe<P>(p0d + L); d.x = read_fe<P>(p0d + 2 * L); d.y = read_fe<P>(p0d + 3 * L);
+  unsigned long long k = start + i;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int b = 63; b >= 0; b--) {
+    xyzz_dbl_nc<P>(acc);
+    if ((k >> b) & 1ull) { Xyzz<P> t = xyzz_from_affine<P>(d); xyzz_add_nc<P>(acc, t); }
+  }
+  { Xyzz<P> t = xyzz_from_affine<P>(p0); xyzz_add_nc<P>(acc, t); }
+  uint32_t* o = out + i * (2 * L);
+  Affine<P> a;
+  if (xyzz_to_affine<P>(acc, a)) { write_fe<P>(o, a.x); write_fe<P>(o + L, a.y); }
+  else { for (int j = 0; j < 2 * L; j++) o[j] = 0xffffffffu; }
+}
+
+template <class C>
+void launch_gen_chain(cudaStream_t s, const uint32_t* p0d, unsigned long long start, size_t n, uint32_t* out) {
+  k_gen_chain<C><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p0d, start, n, out);
+}
+
+template <class C>
+void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, size_t total_out, int log_m,
+                         XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V) {
+  k_reduce_first<C><<<(unsigned)((total_out + 127) / 128), 128, 0, s>>>(buckets, total_out, log_m, U, V);
+}
+template <class C>
+void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin, size_t total_out,
+                        int log_m, int log_M, XyzzMem<typename C::Fp>* Uout, XyzzMem<typename C::Fp>* Vout) {
+  k_reduce_next<C><<<(unsigned)((total_out + 63) / 64), 64, 0, s>>>(Uin, Vin, total_out, log_m, log_M, Uout, Vout);
+}
+template <class C>
+void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out) {
+  k_tail<C><<<(nmsm + 31) / 32, 32, 0, s>>>(Rw, nmsm, W, c, mode, out);
+}
+template <class C>
+void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out) {
+  k_sum_points<C><<<1, 32, 0, s>>>(in, k, in_mode, out_mode, out);
+}
+
+#define ZK_INSTANTIATE_RED(C)                                                                                             \
+  template void launch_reduce_first<C>(cudaStream_t, const XyzzMem<C::Fp>*, size_t, int, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*); \
+  template void launch_reduce_next<C>(cudaStream_t, const XyzzMem<C::Fp>*, const XyzzMem<C::Fp>*, size_t, int, int,        \
+                                      XyzzMem<C::Fp>*, XyzzMem<C::Fp>*);                                                   \
+  template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*);                        \
+  template void launch_sum_points<C>(cudaStream_t, const uint32_t*, int, int, int, uint32_t*);                             \
+  template void launch_gen_chain<C>(cudaStream_t, const uint32_t*, unsigned long long, size_t, uint32_t*);
+
+}  // namespace zk

@@ -1,0 +1,493 @@
+// libzkmsm_b200.so -- thin C host layer + kernel launches for the B200 G1 MSM.
+//
+// Boundary: include/zk_msm_b200.h (the reference's 16 MSM symbols + extensions).  The host layer only
+// moves bytes (H2D of scalars and points, D2H of one point per MSM) and launches kernels; every field
+// and group operation of the path runs on the GPU.  There is no CPU fallback: CUDA errors abort.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/zk_msm_b200.h"
+#include "msm_common.cuh"
+#include "sort.cuh"
+
+using namespace zk;
+
+#define CK(x)                                                                                        \
+  do {                                                                                               \
+    cudaError_t e__ = (x);                                                                           \
+    if (e__ != cudaSuccess) {                                                                        \
+      fprintf(stderr, "[zkmsm_b200] fatal: %s failed at %s:%d: %s\n", #x, __FILE__, __LINE__,        \
+              cudaGetErrorString(e__));                                                              \
+      abort();                                                                                       \
+    }                                                                                                \
+  } while (0)
+
+namespace {
+
+enum Buf {
+  B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS,
+  B_U0, B_V0, B_U1, B_V1, B_OUT, B_COUNT
+};
+constexpr int N_EV = 9;
+constexpr int MAX_DEV = 16;
+
+struct Stats {
+  float ms[9] = {0};
+  int c = 0, W = 0;
+  long long insertions = 0;
+};
+
+struct DeviceCtx {
+  bool ready = false;
+  int dev = 0;
+  cudaStream_t s_main = nullptr, s_copy = nullptr;
+  cudaEvent_t ev[N_EV + 1] = {nullptr};
+  cudaEvent_t ev_points = nullptr;
+  void* buf[B_COUNT] = {nullptr};
+  size_t cap[B_COUNT] = {0};
+  uint32_t* h_out = nullptr;  // pinned staging for results
+  size_t h_out_cap = 0;
+  std::mutex mu;              // one MSM at a time per device (workspaces are shared)
+  Stats stats;
+
+  void* ensure(int which, size_t bytes) {
+    if (bytes > cap[which]) {
+      if (buf[which]) CK(cudaFree(buf[which]));
+      size_t want = bytes + bytes / 8 + 256;
+      CK(cudaMalloc(&buf[which], want));
+      cap[which] = want;
+    }
+    return buf[which];
+  }
+  uint32_t* ensure_host(size_t bytes) {
+    if (bytes > h_out_cap) {
+      if (h_out) CK(cudaFreeHost(h_out));
+      CK(cudaMallocHost((void**)&h_out, bytes));
+      h_out_cap = bytes;
+    }
+    return h_out;
+  }
+};
+
+DeviceCtx g_ctx[MAX_DEV];
+std::mutex g_init_mu;
+std::atomic<int> g_device{-1};
+std::atomic<long long> g_launches{0};  // kernels launched by this library since load
+
+int current_device_choice() {
+  int d = g_device.load();
+  if (d >= 0) return d;
+  const char* e = getenv("ZKB200_DEVICE");
+  d = e ? atoi(e) : 0;
+  g_device.store(d);
+  return d;
+}
+
+DeviceCtx& get_ctx() {
+  int d = current_device_choice();
+  if (d < 0 || d >= MAX_DEV) { fprintf(stderr, "[zkmsm_b200] fatal: bad device index %d\n", d); abort(); }
+  DeviceCtx& cx = g_ctx[d];
+  if (!cx.ready) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (!cx.ready) {
+      int count = 0;
+      cudaError_t e = cudaGetDeviceCount(&count);
+      if (e != cudaSuccess || count == 0) {
+        fprintf(stderr, "[zkmsm_b200] fatal: no CUDA device available (%s); this library has no CPU path\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        abort();
+      }
+      if (d >= count) { fprintf(stderr, "[zkmsm_b200] fatal: device %d requested, %d visible\n", d, count); abort(); }
+      CK(cudaSetDevice(d));
+      cx.dev = d;
+      CK(cudaStreamCreateWithFlags(&cx.s_main, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&cx.s_copy, cudaStreamNonBlocking));
+      for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
+      CK(cudaEventCreateWithFlags(&cx.ev_points, cudaEventDisableTiming));
+      cx.ready = true;
+    }
+  }
+  return cx;
+}
+
+struct DeviceGuard {  // run on our device, then give the caller its own current device back
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    CK(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ilog2_floor(size_t x) { int r = 0; while (x > 1) { x >>= 1; r++; } return r; }
+
+// Window width c for signed digits.  Cost model: n*W insertions (10 Fp mul) + 2*W*2^(c-1) bucket
+// additions (14 Fp mul) + a latency-bound tail; tuned on B200, env override ZKB200_WINDOW.
+int pick_window(size_t n, int nmsm, int nbits) {
+  const char* e = getenv("ZKB200_WINDOW");
+  if (e && atoi(e) > 0) return atoi(e);
+  (void)nmsm;
+  int lg = ilog2_floor(n ? n : 1);
+  int c = lg - 4;
+  if (c < 4) c = 4;
+  if (c > 22) c = 22;
+  // prefer a width that does not waste most of the top window
+  int best = c, bestW = signed_windows(nbits, c);
+  for (int cc = c; cc >= c - 1 && cc >= 2; cc--) {
+    int w = signed_windows(nbits, cc);
+    if (w < bestW) { best = cc; bestW = w; }
+  }
+  return best;
+}
+
+template <class C>
+void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc,
+             int nl, int mont, int out_mode, int window, uint64_t* out) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  using Mem = XyzzMem<P>;
+  if (nl < 1 || nl > 4) { fprintf(stderr, "[zkmsm_b200] fatal: expo_nlimbs = %d unsupported (1..4)\n", nl); abort(); }
+  if (mont && nl != 4) { fprintf(stderr, "[zkmsm_b200] fatal: Montgomery scalars need expo_nlimbs = 4\n"); abort(); }
+  if (nmsm <= 0) return;
+  const int out_coords = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
+  cudaStream_t s = cx.s_main;
+  Stats st;
+  uint32_t* d_out = (uint32_t*)cx.ensure(B_OUT, (size_t)nmsm * 4 * L * 4);
+  uint32_t* h_out = cx.ensure_host((size_t)nmsm * 4 * L * 4);
+
+  const int nbits = mont ? C::Fr::BITS : 64 * nl;
+  int c = 0, W = 0;
+  CK(cudaEventRecord(cx.ev[0], s));
+  if (n == 0) {
+    for (int i = 1; i < N_EV - 1; i++) CK(cudaEventRecord(cx.ev[i], s));
+    g_launches++;
+    launch_tail<C>(s, nullptr, nmsm, 0, 0, out_mode, d_out);
+    CK(cudaGetLastError());
+  } else {
+    c = window > 0 ? window : pick_window(n, nmsm, nbits);
+    if (c < 1) c = 1;
+    if (c > 24) c = 24;
+    W = signed_windows(nbits, c);
+    const uint32_t NB = 1u << (c - 1);
+    const int nseg = nmsm * W;
+    const size_t pairs = (size_t)nseg * n;
+    st.c = c; st.W = W; st.insertions = (long long)pairs;
+
+    // ---- scalars -> device, recode ----
+    const uint64_t* d_scalars = scalars;
+    if (sloc == ZKB200_HOST) {
+      size_t bytes = (size_t)nmsm * n * nl * 8;
+      void* p = cx.ensure(B_SCALARS, bytes);
+      CK(cudaMemcpyAsync(p, scalars, bytes, cudaMemcpyHostToDevice, s));
+      d_scalars = (const uint64_t*)p;
+    }
+    CK(cudaEventRecord(cx.ev[1], s));
+    uint32_t* keys[2] = {(uint32_t*)cx.ensure(B_KEYS0, pairs * 4), (uint32_t*)cx.ensure(B_KEYS1, pairs * 4)};
+    uint32_t* vals[2] = {(uint32_t*)cx.ensure(B_VALS0, pairs * 4), (uint32_t*)cx.ensure(B_VALS1, pairs * 4)};
+    {
+      g_launches++;
+    launch_recode<C>(s, d_scalars, nl, n, nmsm, mont, nbits, c, W, keys[0], vals[0]);
+      CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(cx.ev[2], s));
+
+    // ---- points -> device on the copy stream (overlaps recode + sort) ----
+    const uint32_t* d_points = (const uint32_t*)points;
+    if (ploc == ZKB200_HOST) {
+      size_t bytes = n * (size_t)(2 * L) * 4;
+      void* p = cx.ensure(B_POINTS, bytes);
+      CK(cudaMemcpyAsync(p, points, bytes, cudaMemcpyHostToDevice, cx.s_copy));
+      CK(cudaEventRecord(cx.ev_points, cx.s_copy));
+      d_points = (const uint32_t*)p;
+    }
+
+    // ---- sort pairs by key inside every segment ----
+    const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    uint32_t* cnt = (uint32_t*)cx.ensure(B_CNT, (size_t)nseg * SORT_RADIX * tiles * 4);
+    uint32_t* rowsum = (uint32_t*)cx.ensure(B_ROWSUM, (size_t)nseg * SORT_RADIX * 4);
+    int cur = 0;
+    for (int shift = 0; shift < c; shift += 8) {
+      g_launches += 3;
+      sort_pass(s, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, nseg, shift, cnt, rowsum, tiles);
+      CK(cudaGetLastError());
+      cur ^= 1;
+    }
+    CK(cudaEventRecord(cx.ev[3], s));
+
+    // ---- bucket accumulation ----
+    Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)nseg * NB * sizeof(Mem));
+    CK(cudaMemsetAsync(buckets, 0, (size_t)nseg * NB * sizeof(Mem), s));  // ZZ = 0: every bucket starts at infinity
+    int chunk;
+    {
+      const char* e = getenv("ZKB200_CHUNK");
+      size_t target_threads = 148u * 2048u;
+      size_t ch = e ? (size_t)atoi(e) : (pairs + target_threads - 1) / target_threads;
+      if (ch < 8) ch = 8;
+      if (ch > 512) ch = 512;
+      chunk = (int)ch;
+    }
+    const uint32_t chunks_per_seg = (uint32_t)((n + chunk - 1) / chunk);
+    const size_t nthreads = (size_t)nseg * chunks_per_seg;
+    Mem* heads = (Mem*)cx.ensure(B_HEADS, nthreads * sizeof(Mem));
+    uint32_t* head_keys = (uint32_t*)cx.ensure(B_HEADKEYS, nthreads * 4);
+    if (ploc == ZKB200_HOST) CK(cudaStreamWaitEvent(s, cx.ev_points, 0));
+    CK(cudaEventRecord(cx.ev[4], s));
+    g_launches++;
+    launch_accumulate<C>(s, keys[cur], vals[cur], d_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(cx.ev[5], s));
+    g_launches++;
+    launch_fixup<C>(s, head_keys, heads, nseg, chunks_per_seg, NB, buckets);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(cx.ev[6], s));
+
+    // ---- bucket reduction by levels ----
+    int logS = c - 1;  // entries per segment = 2^logS
+    int log_m = 0;
+    if (logS > 0) {
+      log_m = ilog2_floor(((size_t)nseg << logS) / 65536 + 1);
+      if (log_m < 1) log_m = 1;
+      if (log_m > 5) log_m = 5;
+      if (log_m > logS) log_m = logS;
+    }
+    size_t total_out = (size_t)nseg << (logS - log_m);
+    Mem* U[2] = {(Mem*)cx.ensure(B_U0, total_out * sizeof(Mem)), nullptr};
+    Mem* V[2] = {(Mem*)cx.ensure(B_V0, total_out * sizeof(Mem)), nullptr};
+    g_launches++;
+    launch_reduce_first<C>(s, buckets, total_out, log_m, U[0], V[0]);
+    CK(cudaGetLastError());
+    logS -= log_m;
+    int log_M = log_m;
+    int lv = 0;
+    if (logS > 0) {
+      size_t nxt = (size_t)nseg << (logS > 3 ? logS - 3 : 0);
+      U[1] = (Mem*)cx.ensure(B_U1, nxt * sizeof(Mem));
+      V[1] = (Mem*)cx.ensure(B_V1, nxt * sizeof(Mem));
+    }
+    while (logS > 0) {
+      int lm = logS > 3 ? 3 : logS;
+      total_out = (size_t)nseg << (logS - lm);
+      g_launches++;
+    launch_reduce_next<C>(s, U[lv], V[lv], total_out, lm, log_M, U[lv ^ 1], V[lv ^ 1]);
+      CK(cudaGetLastError());
+      logS -= lm;
+      log_M += lm;
+      lv ^= 1;
+    }
+    CK(cudaEventRecord(cx.ev[7], s));
+
+    // ---- window combination + output conversion ----
+    g_launches++;
+    launch_tail<C>(s, U[lv], nmsm, W, c, out_mode, d_out);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(cx.ev[8], s));
+  CK(cudaStreamSynchronize(s));
+  if (ploc == ZKB200_HOST && n) CK(cudaStreamSynchronize(cx.s_copy));
+  for (int m = 0; m < nmsm; m++)
+    memcpy((uint32_t*)out + (size_t)m * out_coords * L, h_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4);
+  for (int i = 0; i < 8; i++) CK(cudaEventElapsedTime(&st.ms[i], cx.ev[i], cx.ev[i + 1]));
+  CK(cudaEventElapsedTime(&st.ms[8], cx.ev[0], cx.ev[8]));
+  cx.stats = st;
+}
+
+void msm_entry(int curve, int nmsm, long n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc, int nl,
+               int mont, int out_mode, int window, uint64_t* out) {
+  if (n < 0) n = 0;
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  if (curve == ZKB200_BN128) run_msm<Bn254>(cx, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
+  else if (curve == ZKB200_BLS12_381) run_msm<Bls12381>(cx, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
+  else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+}
+
+template <class C>
+void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out) {
+  constexpr int L = C::Fp::L;
+  const int in_coords = in_mode == OUT_XYZZ ? 4 : 3;
+  const int out_coords = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
+  size_t in_bytes = (size_t)(k > 0 ? k : 1) * in_coords * L * 4;
+  uint32_t* d_in = (uint32_t*)cx.ensure(B_SCALARS, in_bytes);
+  uint32_t* d_out = (uint32_t*)cx.ensure(B_OUT, 4 * L * 4);
+  uint32_t* h_out = cx.ensure_host(4 * L * 4);
+  if (k > 0) CK(cudaMemcpyAsync(d_in, in, (size_t)k * in_coords * L * 4, cudaMemcpyHostToDevice, cx.s_main));
+  g_launches++;
+  launch_sum_points<C>(cx.s_main, d_in, k, in_mode, out_mode, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_out, d_out, 4 * L * 4, cudaMemcpyDeviceToHost, cx.s_main));
+  CK(cudaStreamSynchronize(cx.s_main));
+  memcpy(out, h_out, (size_t)out_coords * L * 4);
+}
+
+// ---- IMAD throughput probe ------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) k_imad_probe(uint32_t* out, int iters) {
+  uint32_t a[8], E[8], O[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { a[i] = threadIdx.x * 2654435761u + i * 40503u + 1u; E[i] = a[i] ^ 0x9e3779b9u; O[i] = a[i] + i; }
+  uint32_t b = blockIdx.x + 12345u;
+  if (KIND == 0) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {  // 4 x (two independent 4-product carry chains) = 32 products
+        cmad_row<8, false>(E, a, b);
+        cmad_row<8, false>(O, a, b ^ 0x55u);
+      }
+      b += E[0];
+    }
+  } else if (KIND == 1) {
+    unsigned long long acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = ((unsigned long long)E[i] << 32) | O[i];
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[i]), "r"(b));
+      b += (uint32_t)acc[0];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { E[i] = (uint32_t)acc[i]; O[i] = (uint32_t)(acc[i] >> 32); }
+  } else {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(E[i]) : "r"(a[i]), "r"(b));
+      b += E[0];
+    }
+  }
+  uint32_t x = b;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x ^= E[i] ^ O[i];
+  if (x == 0x12345u) out[0] = x;  // keeps the chains alive without measurable traffic
+}
+
+template <class C>
+void run_gen_chain(DeviceCtx& cx, unsigned long long start, long n, const uint64_t* p0, const uint64_t* d, uint64_t* out,
+                          int out_loc) {
+  constexpr int L = C::Fp::L;
+  if (n <= 0) return;
+  uint32_t* d_in = (uint32_t*)cx.ensure(B_SCALARS, 4 * L * 4);
+  CK(cudaMemcpyAsync(d_in, p0, 2 * L * 4, cudaMemcpyHostToDevice, cx.s_main));
+  CK(cudaMemcpyAsync(d_in + 2 * L, d, 2 * L * 4, cudaMemcpyHostToDevice, cx.s_main));
+  size_t bytes = (size_t)n * 2 * L * 4;
+  uint32_t* d_out = out_loc == ZKB200_DEVICE ? (uint32_t*)out : (uint32_t*)cx.ensure(B_POINTS, bytes);
+  g_launches++;
+  launch_gen_chain<C>(cx.s_main, d_in, start, (size_t)n, d_out);
+  CK(cudaGetLastError());
+  if (out_loc != ZKB200_DEVICE) CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, cx.s_main));
+  CK(cudaStreamSynchronize(cx.s_main));
+}
+
+}  // namespace
+
+// ---- exported C ABI -----------------------------------------------------------------------------------
+#pragma GCC visibility push(default)
+extern "C" {
+
+void zkb200_msm(int curve, int nmsm, long npoints, const uint64_t* scalars, int scalars_loc, const uint64_t* points,
+                int points_loc, int expo_nlimbs, int mont_coeff, int out_mode, int window, uint64_t* out) {
+  msm_entry(curve, nmsm, npoints, scalars, scalars_loc, points, points_loc, expo_nlimbs, mont_coeff, out_mode, window, out);
+}
+
+void zkb200_sum_points(int curve, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out) {
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  if (curve == ZKB200_BN128) run_sum<Bn254>(cx, k, in, in_mode, out_mode, out);
+  else if (curve == ZKB200_BLS12_381) run_sum<Bls12381>(cx, k, in, in_mode, out_mode, out);
+  else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+}
+
+void zkb200_set_device(int device) { g_device.store(device); }
+
+long long zkb200_launch_count(void) { return g_launches.load(); }
+
+void zkb200_gen_chain(int curve, unsigned long long start, long n, const uint64_t* p0_affine, const uint64_t* d_affine,
+                      uint64_t* out, int out_loc) {
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  if (curve == ZKB200_BN128) run_gen_chain<Bn254>(cx, start, n, p0_affine, d_affine, out, out_loc);
+  else if (curve == ZKB200_BLS12_381) run_gen_chain<Bls12381>(cx, start, n, p0_affine, d_affine, out, out_loc);
+  else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+}
+
+void zkb200_last_stats(float phase_ms[9], int* window_c, int* nwindows, long long* insertions) {
+  DeviceCtx& cx = get_ctx();
+  std::lock_guard<std::mutex> lk(cx.mu);
+  if (phase_ms) memcpy(phase_ms, cx.stats.ms, sizeof(float) * 9);
+  if (window_c) *window_c = cx.stats.c;
+  if (nwindows) *nwindows = cx.stats.W;
+  if (insertions) *insertions = cx.stats.insertions;
+}
+
+double zkb200_imad_peak(int kind, int iters) {
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  if (iters < 1) iters = 1;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cx.dev));
+  int blocks = prop.multiProcessorCount * 8;
+  uint32_t* d = (uint32_t*)cx.ensure(B_OUT, 256);
+  cudaStream_t s = cx.s_main;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(cx.ev[0], s));
+    if (kind == 0) k_imad_probe<0><<<blocks, 256, 0, s>>>(d, iters);
+    else if (kind == 1) k_imad_probe<1><<<blocks, 256, 0, s>>>(d, iters);
+    else k_imad_probe<2><<<blocks, 256, 0, s>>>(d, iters);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(cx.ev[1], s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, cx.ev[0], cx.ev[1]));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  double products = (double)blocks * 256.0 * (double)iters * 32.0;
+  return products / (best * 1e-3);
+}
+
+const char* zkb200_version(void) { return "zkmsm_b200 0.1 (sm_100a)"; }
+
+#define ZK_REF_SYMBOLS(NAME, ID)                                                                                      \
+  void NAME##_G1_proj_MSM_std_coeff_proj_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {      \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_PROJ, 0, t); }                                     \
+  void NAME##_G1_proj_MSM_mont_coeff_proj_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {     \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 1, OUT_PROJ, 0, t); }                                     \
+  void NAME##_G1_proj_MSM_std_coeff_affine_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {    \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_AFFINE, 0, t); }                                   \
+  void NAME##_G1_proj_MSM_mont_coeff_affine_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {   \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 1, OUT_AFFINE, 0, t); }                                   \
+  void NAME##_G1_jac_MSM_std_coeff_jac_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {        \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_JAC, 0, t); }                                      \
+  void NAME##_G1_jac_MSM_mont_coeff_jac_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {       \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 1, OUT_JAC, 0, t); }                                      \
+  void NAME##_G1_jac_MSM_std_coeff_affine_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {     \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_AFFINE, 0, t); }                                   \
+  void NAME##_G1_jac_MSM_mont_coeff_affine_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {    \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 1, OUT_AFFINE, 0, t); }                                   \
+  void NAME##_G1_proj_MSM_std_coeff_proj_out_variable(int n, const uint64_t* e, const uint64_t* g, uint64_t* t,       \
+                                                      int nl, int ws) {                                               \
+    if (ws < 1 || ws > 64) { fprintf(stderr, "[zkmsm_b200] fatal: window_size %d out of range\n", ws); abort(); }     \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_PROJ, ws, t); }                                    \
+  void NAME##_G1_jac_MSM_std_coeff_jac_out_variable(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl, \
+                                                    int ws) {                                                         \
+    if (ws < 1 || ws > 64) { fprintf(stderr, "[zkmsm_b200] fatal: window_size %d out of range\n", ws); abort(); }     \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_JAC, ws, t); }
+
+ZK_REF_SYMBOLS(bn128, ZKB200_BN128)
+ZK_REF_SYMBOLS(bls12_381, ZKB200_BLS12_381)
+
+}  // extern "C"
+#pragma GCC visibility pop
