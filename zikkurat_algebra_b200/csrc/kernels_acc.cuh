@@ -93,31 +93,51 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   head_keys[t] = head_key;
 }
 
-// Fold the per-chunk head sums into their buckets.  Consecutive chunks of a segment whose head runs
-// carry the same key form a group; the first thread of a group adds the whole group (sequentially).
+// Fold the per-chunk head sums into their buckets: a segmented tree reduction, FIXUP_FAN entries per
+// thread and level.  Input: per segment T_in (key, partial sum) records sorted by key (key 0 = empty).
+// Exactly like k_accumulate, a thread's first run may continue the previous thread's and is handed to
+// the next level (heads_out); every other run started inside this thread's slice, so this thread is
+// the only one of the level to touch that bucket and adds its sum in place.  On the last level
+// (one thread per segment) everything goes to the buckets.  Depth is log_FAN(T) whatever the scalar
+// distribution (a window holding one single key is the worst case).
+
 template <class C>
 __global__ void __launch_bounds__(128)
-k_fixup(const uint32_t* __restrict__ head_keys, const XyzzMem<typename C::Fp>* __restrict__ heads,
-        int nseg, uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets) {
+k_fixup_level(const uint32_t* __restrict__ keys_in, const XyzzMem<typename C::Fp>* __restrict__ heads_in, uint32_t T_in,
+              uint32_t* __restrict__ keys_out, XyzzMem<typename C::Fp>* __restrict__ heads_out, uint32_t T_out, int nseg,
+              uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets, int last) {
   using P = typename C::Fp;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)nseg * chunks_per_seg) return;
-  uint32_t seg = (uint32_t)(t / chunks_per_seg);
-  uint32_t j = (uint32_t)(t - (size_t)seg * chunks_per_seg);
-  uint32_t key = head_keys[t];
-  if (key == 0) return;
-  if (j > 0 && head_keys[t - 1] == key) return;  // not the group leader
-  XyzzMem<P>* b = buckets + (size_t)seg * NB + (key - 1);
-  Xyzz<P> acc = load_xyzz<P>(b);
-  size_t u = t;
-  uint32_t jj = j;
-  do {
-    acc = xyzz_add<P>(acc, load_xyzz<P>(heads + u));
-    u++; jj++;
-  } while (jj < chunks_per_seg && head_keys[u] == key);
-  store_xyzz<P>(b, acc);
+  if (t >= (size_t)nseg * T_out) return;
+  uint32_t seg = (uint32_t)(t / T_out);
+  uint32_t j = (uint32_t)(t - (size_t)seg * T_out);
+  uint32_t lo = j * FIXUP_FAN, hi = lo + FIXUP_FAN < T_in ? lo + FIXUP_FAN : T_in;
+  const uint32_t* kp = keys_in + (size_t)seg * T_in;
+  const XyzzMem<P>* hp = heads_in + (size_t)seg * T_in;
+  XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
+  Xyzz<P> acc = xyzz_inf<P>();
+  uint32_t cur = 0, head_key = 0;
+  bool head_open = !last;
+  for (uint32_t e = lo; e < hi; e++) {
+    uint32_t key = kp[e];
+    if (key == 0) continue;
+    if (key != cur) {
+      if (cur != 0) {
+        if (head_open) { store_xyzz<P>(heads_out + t, acc); head_key = cur; head_open = false; }
+        else store_xyzz<P>(bseg + (cur - 1), xyzz_add<P>(load_xyzz<P>(bseg + (cur - 1)), acc));
+      }
+      cur = key;
+      acc = load_xyzz<P>(hp + e);
+    } else {
+      acc = xyzz_add<P>(acc, load_xyzz<P>(hp + e));
+    }
+  }
+  if (cur != 0) {
+    if (head_open) { store_xyzz<P>(heads_out + t, acc); head_key = cur; }
+    else store_xyzz<P>(bseg + (cur - 1), xyzz_add<P>(load_xyzz<P>(bseg + (cur - 1)), acc));
+  }
+  if (!last) keys_out[t] = head_key;
 }
-
 
 template <class C>
 void launch_recode(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int nbits, int c, int W,
@@ -134,16 +154,19 @@ void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* val
                                                                     buckets, heads, head_keys);
 }
 template <class C>
-void launch_fixup(cudaStream_t s, const uint32_t* head_keys, const XyzzMem<typename C::Fp>* heads, int nseg,
-                  uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets) {
-  size_t nthreads = (size_t)nseg * chunks_per_seg;
-  k_fixup<C><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(head_keys, heads, nseg, chunks_per_seg, NB, buckets);
+void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<typename C::Fp>* heads_in, uint32_t T_in,
+                        uint32_t* keys_out, XyzzMem<typename C::Fp>* heads_out, uint32_t T_out, int nseg, uint32_t NB,
+                        XyzzMem<typename C::Fp>* buckets, int last) {
+  size_t nthreads = (size_t)nseg * T_out;
+  k_fixup_level<C><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys_in, heads_in, T_in, keys_out, heads_out, T_out, nseg,
+                                                                     NB, buckets, last);
 }
 
 #define ZK_INSTANTIATE_ACC(C)                                                                                              \
   template void launch_recode<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, int, uint32_t*, uint32_t*); \
   template void launch_accumulate<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,     \
                                      uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);                      \
-  template void launch_fixup<C>(cudaStream_t, const uint32_t*, const XyzzMem<C::Fp>*, int, uint32_t, uint32_t, XyzzMem<C::Fp>*);
+  template void launch_fixup_level<C>(cudaStream_t, const uint32_t*, const XyzzMem<C::Fp>*, uint32_t, uint32_t*,           \
+                                      XyzzMem<C::Fp>*, uint32_t, int, uint32_t, XyzzMem<C::Fp>*, int);
 
 }  // namespace zk

@@ -70,6 +70,8 @@ ZK_D Affine<P> load_affine(const uint32_t* __restrict__ pts, uint32_t i) {
 }
 
 
+constexpr int FIXUP_FAN = 8;  // fan-in per level of the head fix-up tree (kernels_acc.cuh)
+
 enum OutMode : int { OUT_PROJ = 0, OUT_JAC = 1, OUT_AFFINE = 2, OUT_XYZZ = 3 };
 
 // ---- host-side launchers (defined next to their kernels, explicitly instantiated per curve) -------------
@@ -78,8 +80,9 @@ template <class C> void launch_recode(cudaStream_t s, const uint64_t* scalars, i
 template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
                                           size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
                                           XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys);
-template <class C> void launch_fixup(cudaStream_t s, const uint32_t* head_keys, const XyzzMem<typename C::Fp>* heads, int nseg,
-                                     uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets);
+template <class C> void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<typename C::Fp>* heads_in,
+                                           uint32_t T_in, uint32_t* keys_out, XyzzMem<typename C::Fp>* heads_out, uint32_t T_out,
+                                           int nseg, uint32_t NB, XyzzMem<typename C::Fp>* buckets, int last);
 template <class C> void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, size_t total_out, int log_m,
                                             XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V);
 template <class C> void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin,

@@ -31,7 +31,7 @@ using namespace zk;
 namespace {
 
 enum Buf {
-  B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS,
+  B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
   B_U0, B_V0, B_U1, B_V1, B_OUT, B_COUNT
 };
 constexpr int N_EV = 9;
@@ -127,21 +127,21 @@ struct DeviceGuard {  // run on our device, then give the caller its own current
 
 int ilog2_floor(size_t x) { int r = 0; while (x > 1) { x >>= 1; r++; } return r; }
 
-// Window width c for signed digits.  Cost model: n*W insertions (10 Fp mul) + 2*W*2^(c-1) bucket
-// additions (14 Fp mul) + a latency-bound tail; tuned on B200, env override ZKB200_WINDOW.
+// Window width c for signed digits: minimise the Fp-multiplication count of the two throughput phases,
+//   W(c) * ( n * 10  +  2^(c-1) * 2 * 14 ),   W(c) = ceil((nbits+1)/c)
+// (n*W bucket insertions at 10 mul, 2 additions of 14 mul per bucket in the reduction).  Widths whose
+// top window would be nearly empty lose automatically because they pay a whole extra window.
+// Override: $ZKB200_WINDOW.
 int pick_window(size_t n, int nmsm, int nbits) {
   const char* e = getenv("ZKB200_WINDOW");
   if (e && atoi(e) > 0) return atoi(e);
   (void)nmsm;
-  int lg = ilog2_floor(n ? n : 1);
-  int c = lg - 4;
-  if (c < 4) c = 4;
-  if (c > 22) c = 22;
-  // prefer a width that does not waste most of the top window
-  int best = c, bestW = signed_windows(nbits, c);
-  for (int cc = c; cc >= c - 1 && cc >= 2; cc--) {
-    int w = signed_windows(nbits, cc);
-    if (w < bestW) { best = cc; bestW = w; }
+  int best = 1;
+  double best_cost = 1e300;
+  for (int c = 1; c <= 24; c++) {
+    double W = (double)signed_windows(nbits, c);
+    double cost = W * ((double)n * 10.0 + (double)(1ull << (c - 1)) * 28.0);
+    if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
 }
@@ -242,9 +242,23 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     launch_accumulate<C>(s, keys[cur], vals[cur], d_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
     CK(cudaGetLastError());
     CK(cudaEventRecord(cx.ev[5], s));
-    g_launches++;
-    launch_fixup<C>(s, head_keys, heads, nseg, chunks_per_seg, NB, buckets);
-    CK(cudaGetLastError());
+    {  // fold the chunk heads into the buckets: log_FAN(chunks_per_seg) tiny levels
+      uint32_t T = chunks_per_seg;
+      size_t cap2 = (size_t)nseg * ((T + FIXUP_FAN - 1) / FIXUP_FAN);
+      Mem* hb[2] = {heads, (Mem*)cx.ensure(B_HEADS2, cap2 * sizeof(Mem))};
+      uint32_t* kb[2] = {head_keys, (uint32_t*)cx.ensure(B_HEADKEYS2, cap2 * 4)};
+      int src = 0;
+      for (;;) {
+        uint32_t T_out = (T + FIXUP_FAN - 1) / FIXUP_FAN;
+        int last = T_out == 1;
+        g_launches++;
+        launch_fixup_level<C>(s, kb[src], hb[src], T, kb[src ^ 1], hb[src ^ 1], T_out, nseg, NB, buckets, last);
+        CK(cudaGetLastError());
+        if (last) break;
+        T = T_out;
+        src ^= 1;
+      }
+    }
     CK(cudaEventRecord(cx.ev[6], s));
 
     // ---- bucket reduction by levels ----
