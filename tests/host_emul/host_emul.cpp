@@ -55,6 +55,7 @@ static Xyzz<P> sum_list(long n, const uint64_t* pts, const uint8_t* neg) {
     st<C::Fp>(t, fe_sub<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b))); }                                                  \
   extern "C" void he_##NAME##_fp_neg(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_neg<C::Fp>(ld<C::Fp>(a))); } \
   extern "C" void he_##NAME##_fp_inv(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_inv<C::Fp>(ld<C::Fp>(a))); } \
+  extern "C" void he_##NAME##_fp_inv_fermat(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_inv_fermat<C::Fp>(ld<C::Fp>(a))); } \
   extern "C" void he_##NAME##_fr_to_std(const uint64_t* a, uint64_t* t) {                                       \
     st<C::Fr>(t, fe_from_mont<C::Fr>(ld<C::Fr>(a))); }                                                          \
   extern "C" void he_##NAME##_sum_list(long n, const uint64_t* pts, const uint8_t* neg, uint64_t* t_aff) {      \

@@ -47,9 +47,10 @@ def test_fp_ops(he, curve):
         assert dec(refs.call3(he, f"he_{curve}_fp_add", A, B, L)) == (a + b) % cv.p
         assert dec(refs.call3(he, f"he_{curve}_fp_sub", A, B, L)) == (a - b) % cv.p
         assert dec(refs.call2(he, f"he_{curve}_fp_neg", A, L)) == (-a) % cv.p
-    for a in [1, 2, cv.p - 1] + [rng.randrange(1, cv.p) for _ in range(20)]:
+    for a in [1, 2, 3, 4, cv.p - 1, cv.p - 2, (cv.p + 1) // 2, 1 << 200] + [rng.randrange(1, cv.p) for _ in range(300)]:
         A = _arr(cv.fp_to_bytes(a))
         assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv", A, L).tobytes()) == pow(a, -1, cv.p)
+        assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv_fermat", A, L).tobytes()) == pow(a, -1, cv.p)
 
 
 @pytest.mark.parametrize("curve", CURVES)

@@ -207,9 +207,9 @@ ZK_HD Fe<P> fe_from_mont(const Fe<P>& a) {
   return fe_mul<P>(a, one_std);
 }
 
-// a^(p-2) by square-and-multiply over the constant exponent (used once per MSM for to_affine).
+// a^(p-2) by square-and-multiply over the constant exponent (kept as a cross-check of fe_inv).
 template <class P>
-ZK_HD Fe<P> fe_inv(const Fe<P>& a) {
+ZK_HD Fe<P> fe_inv_fermat(const Fe<P>& a) {
   constexpr int L = P::L;
   Fe<P> acc = fe_one<P>();
   bool started = false;
@@ -224,6 +224,72 @@ ZK_HD Fe<P> fe_inv(const Fe<P>& a) {
     }
   }
   return acc;
+}
+
+// ---- inversion by the binary extended Euclidean algorithm -------------------------------------------
+// Same method as the reference (bn128_Fp_std_inv, lib/cbits/curves/fields/std/bn128_Fp_std.c:252-315,
+// followed by a multiplication by R^3, lib/cbits/curves/fields/mont/bn128_Fp_mont.c:201-204): the
+// Montgomery residue x = a*R is inverted as a plain integer mod p, and x^-1 * R^3 * R^-1 = a^-1 * R.
+// ~2*bits shift/subtract steps on L-limb integers: about 6x shorter than the Fermat chain for one thread.
+template <int L>
+ZK_HD void big_shr1(uint32_t* a, uint32_t top_in) {  // a = (top_in:a) >> 1
+#pragma unroll
+  for (int i = 0; i < L - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+  a[L - 1] = (a[L - 1] >> 1) | (top_in << 31);
+}
+template <class P>
+ZK_HD void halve_mod(uint32_t* x) {  // x = x/2 mod p  (x < p)
+  constexpr int L = P::L;
+  uint32_t odd = (x[0] & 1u) ? 0xffffffffu : 0u;
+  x[0] = add_cc(x[0], P::mod(0) & odd);
+#pragma unroll
+  for (int i = 1; i < L; i++) x[i] = addc_cc(x[i], P::mod(i) & odd);
+  uint32_t top = addc(0u, 0u);
+  big_shr1<L>(x, top);
+}
+template <int L>
+ZK_HD bool big_is_one(const uint32_t* a) {
+  uint32_t o = a[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < L; i++) o |= a[i];
+  return o == 0;
+}
+// a -= b, returns true when it borrowed
+template <int L>
+ZK_HD bool big_sub_borrow(uint32_t* a, const uint32_t* b) {
+  a[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < L; i++) a[i] = subc_cc(a[i], b[i]);
+  return subc(0u, 0u) != 0u;
+}
+template <int L>
+ZK_HD bool big_lt(const uint32_t* a, const uint32_t* b) {  // a < b
+  uint32_t t = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < L; i++) t = subc_cc(a[i], b[i]);
+  (void)t;
+  return subc(0u, 0u) != 0u;
+}
+template <class P>
+ZK_HD Fe<P> fe_inv(const Fe<P>& a) {  // a != 0, canonical; returns the Montgomery form of 1/a
+  constexpr int L = P::L;
+  uint32_t u[L], v[L];
+  Fe<P> x1 = fe_zero<P>(), x2 = fe_zero<P>();
+  x1.l[0] = 1;
+#pragma unroll
+  for (int i = 0; i < L; i++) { u[i] = a.l[i]; v[i] = P::mod(i); }
+  for (int guard = 0; guard < 4 * 32 * L; guard++) {
+    if (big_is_one<L>(u) || big_is_one<L>(v)) break;
+    while ((u[0] & 1u) == 0) { big_shr1<L>(u, 0u); halve_mod<P>(x1.l); }
+    while ((v[0] & 1u) == 0) { big_shr1<L>(v, 0u); halve_mod<P>(x2.l); }
+    if (!big_lt<L>(u, v)) { big_sub_borrow<L>(u, v); x1 = fe_sub<P>(x1, x2); }
+    else { big_sub_borrow<L>(v, u); x2 = fe_sub<P>(x2, x1); }
+  }
+  Fe<P> r = big_is_one<L>(u) ? x1 : x2;
+  Fe<P> r3;
+#pragma unroll
+  for (int i = 0; i < L; i++) r3.l[i] = P::r3(i);
+  return fe_mul<P>(r, r3);
 }
 
 }  // namespace zk

@@ -3,6 +3,7 @@
 //   lib/cbits/curves/g1/proj/bn128_G1_proj.c:520-561 (digit extraction + bucket accumulation)
 //   lib/cbits/curves/g1/proj/bn128_G1_proj.c:629-643 (Fr Montgomery -> standard conversion)
 #pragma once
+#include "ec_team.cuh"
 #include "msm_common.cuh"
 
 namespace zk {
@@ -101,14 +102,18 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
 // (one thread per segment) everything goes to the buckets.  Depth is log_FAN(T) whatever the scalar
 // distribution (a window holding one single key is the worst case).
 
+template <class P>
+__device__ __noinline__ void xyzz_add_tm(const Team& tm, Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add_team<P>(tm, a, b); }
+
 template <class C>
 __global__ void __launch_bounds__(128)
 k_fixup_level(const uint32_t* __restrict__ keys_in, const XyzzMem<typename C::Fp>* __restrict__ heads_in, uint32_t T_in,
               uint32_t* __restrict__ keys_out, XyzzMem<typename C::Fp>* __restrict__ heads_out, uint32_t T_out, int nseg,
               uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets, int last) {
   using P = typename C::Fp;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;  // one 4-lane team per output entry
   if (t >= (size_t)nseg * T_out) return;
+  Team tm;
   uint32_t seg = (uint32_t)(t / T_out);
   uint32_t j = (uint32_t)(t - (size_t)seg * T_out);
   uint32_t lo = j * FIXUP_FAN, hi = lo + FIXUP_FAN < T_in ? lo + FIXUP_FAN : T_in;
@@ -117,26 +122,33 @@ k_fixup_level(const uint32_t* __restrict__ keys_in, const XyzzMem<typename C::Fp
   XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
   Xyzz<P> acc = xyzz_inf<P>();
   uint32_t cur = 0, head_key = 0;
+  // The slice's first run is handed to the next level only when it really continues the previous
+  // slice's last run (same key just before `lo`); otherwise nobody else on this level owns that
+  // bucket and the sum is folded in right here, so the upper levels stay empty for ordinary inputs.
+  uint32_t prev_key = (lo > 0 && lo < T_in) ? kp[lo - 1] : 0u;
   bool head_open = !last;
-  for (uint32_t e = lo; e < hi; e++) {
-    uint32_t key = kp[e];
+  for (uint32_t e = lo; e <= hi; e++) {
+    uint32_t key = e < hi ? kp[e] : 0xffffffffu;  // sentinel closes the last run
     if (key == 0) continue;
     if (key != cur) {
       if (cur != 0) {
-        if (head_open) { store_xyzz<P>(heads_out + t, acc); head_key = cur; head_open = false; }
-        else store_xyzz<P>(bseg + (cur - 1), xyzz_add<P>(load_xyzz<P>(bseg + (cur - 1)), acc));
+        if (head_open && cur == prev_key) {
+          if (tm.t == 0) store_xyzz<P>(heads_out + t, acc);
+          head_key = cur;
+          head_open = false;
+        } else {
+          head_open = false;
+          xyzz_add_tm<P>(tm, acc, load_xyzz<P>(bseg + (cur - 1)));
+          if (tm.t == 0) store_xyzz<P>(bseg + (cur - 1), acc);
+        }
       }
       cur = key;
-      acc = load_xyzz<P>(hp + e);
+      if (e < hi) acc = load_xyzz<P>(hp + e);
     } else {
-      acc = xyzz_add<P>(acc, load_xyzz<P>(hp + e));
+      xyzz_add_tm<P>(tm, acc, load_xyzz<P>(hp + e));
     }
   }
-  if (cur != 0) {
-    if (head_open) { store_xyzz<P>(heads_out + t, acc); head_key = cur; }
-    else store_xyzz<P>(bseg + (cur - 1), xyzz_add<P>(load_xyzz<P>(bseg + (cur - 1)), acc));
-  }
-  if (!last) keys_out[t] = head_key;
+  if (!last && tm.t == 0) keys_out[t] = head_key;
 }
 
 template <class C>
@@ -154,15 +166,26 @@ void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* val
                                                                     buckets, heads, head_keys);
 }
 template <class C>
+int accumulate_resident_threads() {  // threads of k_accumulate<C> that fit on the whole GPU at once
+  int dev = 0, sms = 0, blocks = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C>, 128, 0);
+  if (blocks < 1) blocks = 1;
+  return sms * blocks * 128;
+}
+
+template <class C>
 void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<typename C::Fp>* heads_in, uint32_t T_in,
                         uint32_t* keys_out, XyzzMem<typename C::Fp>* heads_out, uint32_t T_out, int nseg, uint32_t NB,
                         XyzzMem<typename C::Fp>* buckets, int last) {
-  size_t nthreads = (size_t)nseg * T_out;
+  size_t nthreads = (size_t)nseg * T_out * 4;
   k_fixup_level<C><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys_in, heads_in, T_in, keys_out, heads_out, T_out, nseg,
                                                                      NB, buckets, last);
 }
 
 #define ZK_INSTANTIATE_ACC(C)                                                                                              \
+  template int accumulate_resident_threads<C>();                                                                          \
   template void launch_recode<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, int, uint32_t*, uint32_t*); \
   template void launch_accumulate<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,     \
                                      uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);                      \

@@ -3,6 +3,7 @@
 //   lib/cbits/curves/g1/proj/bn128_G1_proj.c:565-582 (running sums, Horner over windows)
 //   lib/cbits/curves/g1/proj/bn128_G1_proj.c:132-144 (to_affine)
 #pragma once
+#include "ec_team.cuh"
 #include "msm_common.cuh"
 
 namespace zk {
@@ -13,6 +14,11 @@ template <class P>
 __device__ __noinline__ void xyzz_add_nc(Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add<P>(a, b); }
 template <class P>
 __device__ __noinline__ void xyzz_dbl_nc(Xyzz<P>& a) { a = xyzz_dbl<P>(a); }
+// 4-lane team versions (ec_team.cuh), also out of line
+template <class P>
+__device__ __noinline__ void xyzz_add_tm(const Team& tm, Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add_team<P>(tm, a, b); }
+template <class P>
+__device__ __noinline__ void xyzz_dbl_tm(const Team& tm, Xyzz<P>& a) { a = xyzz_dbl_team<P>(tm, a); }
 
 // ---- K5: bucket reduction  sum_b (b+1) * B[b]  by levels ------------------------------------------------
 // Invariant after every level:  R_seg = sum_t ( U[t] + M * t * V[t] ),  t = 0..S-1.
@@ -41,22 +47,25 @@ k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typ
               size_t total_out, int log_m, int log_M, XyzzMem<typename C::Fp>* __restrict__ Uout,
               XyzzMem<typename C::Fp>* __restrict__ Vout) {
   using P = typename C::Fp;
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;  // one 4-lane team per output entry
   if (g >= total_out) return;
+  Team tm;
   const XyzzMem<P>* u = Uin + (g << log_m);
   const XyzzMem<P>* v = Vin + (g << log_m);
   Xyzz<P> run = xyzz_inf<P>(), acc = xyzz_inf<P>(), usum = xyzz_inf<P>();
   for (int i = (1 << log_m) - 1; i >= 1; i--) {
-    xyzz_add_nc<P>(run, load_xyzz<P>(v + i));
-    xyzz_add_nc<P>(acc, run);
-    xyzz_add_nc<P>(usum, load_xyzz<P>(u + i));
+    xyzz_add_tm<P>(tm, run, load_xyzz<P>(v + i));
+    xyzz_add_tm<P>(tm, acc, run);
+    xyzz_add_tm<P>(tm, usum, load_xyzz<P>(u + i));
   }
-  xyzz_add_nc<P>(run, load_xyzz<P>(v));
-  xyzz_add_nc<P>(usum, load_xyzz<P>(u));
-  for (int d = 0; d < log_M; d++) xyzz_dbl_nc<P>(acc);
-  xyzz_add_nc<P>(usum, acc);
-  store_xyzz<P>(Uout + g, usum);
-  store_xyzz<P>(Vout + g, run);
+  xyzz_add_tm<P>(tm, run, load_xyzz<P>(v));
+  xyzz_add_tm<P>(tm, usum, load_xyzz<P>(u));
+  for (int d = 0; d < log_M; d++) xyzz_dbl_tm<P>(tm, acc);
+  xyzz_add_tm<P>(tm, usum, acc);
+  if (tm.t == 0) {
+    store_xyzz<P>(Uout + g, usum);
+    store_xyzz<P>(Vout + g, run);
+  }
 }
 
 // ---- K6 + K7: window combination (Horner) and output conversion ------------------------------------------
@@ -88,22 +97,23 @@ ZK_D void write_result(uint32_t* o, const Xyzz<P>& acc, int mode) {
     write_fe<P>(o, X); write_fe<P>(o + L, Y); write_fe<P>(o + 2 * L, Z);
   }
 }
-// one thread per MSM of the batch; Rw[msm*W + w] = window sums; out record stride = 4L words
+// one 4-lane team per MSM of the batch; Rw[msm*W + w] = window sums; out record stride = 4L words
 template <class C>
-__global__ void k_tail(const XyzzMem<typename C::Fp>* __restrict__ Rw, int nmsm, int W, int c, int mode,
-                       uint32_t* __restrict__ out) {
+__global__ void __launch_bounds__(32)
+k_tail(const XyzzMem<typename C::Fp>* __restrict__ Rw, int nmsm, int W, int c, int mode, uint32_t* __restrict__ out) {
   using P = typename C::Fp;
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   if (m >= nmsm) return;
+  Team tm;
   Xyzz<P> acc = xyzz_inf<P>();
   if (W > 0) {
     acc = load_xyzz<P>(Rw + (size_t)m * W + (W - 1));
     for (int w = W - 2; w >= 0; w--) {
-      for (int d = 0; d < c; d++) xyzz_dbl_nc<P>(acc);
-      xyzz_add_nc<P>(acc, load_xyzz<P>(Rw + (size_t)m * W + w));
+      for (int d = 0; d < c; d++) xyzz_dbl_tm<P>(tm, acc);
+      xyzz_add_tm<P>(tm, acc, load_xyzz<P>(Rw + (size_t)m * W + w));
     }
   }
-  write_result<P>(out + (size_t)m * (4 * P::L), acc, mode);
+  if (tm.t == 0) write_result<P>(out + (size_t)m * (4 * P::L), acc, mode);
 }
 
 // sum of k group elements given in one of the reference's representations (multi-GPU combine, K8)
@@ -112,7 +122,8 @@ template <class C>
 __global__ void k_sum_points(const uint32_t* __restrict__ in, int k, int in_mode, int out_mode, uint32_t* __restrict__ out) {
   using P = typename C::Fp;
   constexpr int L = P::L;
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 4) return;
+  Team tm;
   Xyzz<P> acc = xyzz_inf<P>();
   for (int i = 0; i < k; i++) {
     Xyzz<P> p;
@@ -124,9 +135,9 @@ __global__ void k_sum_points(const uint32_t* __restrict__ in, int k, int in_mode
       Fe<P> X = read_fe<P>(s), Y = read_fe<P>(s + L), Z = read_fe<P>(s + 2 * L);
       p = (in_mode == OUT_PROJ) ? xyzz_from_proj<P>(X, Y, Z) : xyzz_from_jac<P>(X, Y, Z);
     }
-    xyzz_add_nc<P>(acc, p);
+    xyzz_add_tm<P>(tm, acc, p);
   }
-  write_result<P>(out, acc, out_mode);
+  if (tm.t == 0) write_result<P>(out, acc, out_mode);
 }
 
 
@@ -167,11 +178,11 @@ void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets,
 template <class C>
 void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin, size_t total_out,
                         int log_m, int log_M, XyzzMem<typename C::Fp>* Uout, XyzzMem<typename C::Fp>* Vout) {
-  k_reduce_next<C><<<(unsigned)((total_out + 63) / 64), 64, 0, s>>>(Uin, Vin, total_out, log_m, log_M, Uout, Vout);
+  k_reduce_next<C><<<(unsigned)((total_out * 4 + 127) / 128), 128, 0, s>>>(Uin, Vin, total_out, log_m, log_M, Uout, Vout);
 }
 template <class C>
 void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out) {
-  k_tail<C><<<(nmsm + 31) / 32, 32, 0, s>>>(Rw, nmsm, W, c, mode, out);
+  k_tail<C><<<(nmsm * 4 + 31) / 32, 32, 0, s>>>(Rw, nmsm, W, c, mode, out);
 }
 template <class C>
 void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out) {

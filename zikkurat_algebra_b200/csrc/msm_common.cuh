@@ -80,6 +80,7 @@ template <class C> void launch_recode(cudaStream_t s, const uint64_t* scalars, i
 template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
                                           size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
                                           XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys);
+template <class C> int accumulate_resident_threads();
 template <class C> void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<typename C::Fp>* heads_in,
                                            uint32_t T_in, uint32_t* keys_out, XyzzMem<typename C::Fp>* heads_out, uint32_t T_out,
                                            int nseg, uint32_t NB, XyzzMem<typename C::Fp>* buckets, int last);

@@ -223,14 +223,26 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // ---- bucket accumulation ----
     Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)nseg * NB * sizeof(Mem));
     CK(cudaMemsetAsync(buckets, 0, (size_t)nseg * NB * sizeof(Mem), s));  // ZZ = 0: every bucket starts at infinity
+    // Sorted pairs per thread.  The grid is sized to a whole number of waves of resident threads so
+    // that all SMs drain together (a partial last wave costs a full chunk time): chunk ~ 48 insertions.
     int chunk;
     {
       const char* e = getenv("ZKB200_CHUNK");
-      size_t target_threads = 148u * 2048u;
-      size_t ch = e ? (size_t)atoi(e) : (pairs + target_threads - 1) / target_threads;
-      if (ch < 8) ch = 8;
-      if (ch > 512) ch = 512;
-      chunk = (int)ch;
+      if (e && atoi(e) > 0) {
+        chunk = atoi(e);
+      } else {
+        static int resident_cache[2] = {0, 0};
+        int& resident = resident_cache[C::Fp::L == 8 ? 0 : 1];
+        if (resident == 0) resident = accumulate_resident_threads<C>();
+        double waves = (double)pairs / ((double)resident * 48.0);
+        size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
+        size_t per_seg_threads = ((size_t)resident * nw) / (size_t)nseg;   // threads available to one segment
+        if (per_seg_threads < 1) per_seg_threads = 1;
+        size_t ch = (n + per_seg_threads - 1) / per_seg_threads;
+        if (ch < 8) ch = 8;
+        if (ch > 1024) ch = 1024;
+        chunk = (int)ch;
+      }
     }
     const uint32_t chunks_per_seg = (uint32_t)((n + chunk - 1) / chunk);
     const size_t nthreads = (size_t)nseg * chunks_per_seg;
