@@ -97,9 +97,47 @@ ZK_HD Xyzz<P> xyzz_dbl(const Xyzz<P>& a) {
   return r;
 }
 
-// acc += p   (p affine, already known not to be infinity).  The bucket-insertion primitive.
+// same operation with every multiplication out of line (fe_mul_call): small code, same arithmetic
 template <class P>
+ZK_HD void xyzz_madd_calls(Xyzz<P>& acc, const Affine<P>& p) {
+  if (xyzz_is_inf<P>(acc)) {
+    acc = xyzz_from_affine<P>(p);
+    return;
+  }
+  Fe<P> Pd = fe_sub<P>(fe_mul_call<P>(p.x, acc.ZZ), acc.X);
+  Fe<P> R = fe_sub<P>(fe_mul_call<P>(p.y, acc.ZZZ), acc.Y);
+  if (fe_is_zero<P>(Pd)) {
+    if (fe_is_zero<P>(R)) {  // same point: double (mdbl-2008-s-1)
+      Fe<P> U = fe_dbl<P>(p.y);
+      Fe<P> V = fe_mul_call<P>(U, U);
+      Fe<P> W = fe_mul_call<P>(U, V);
+      Fe<P> S = fe_mul_call<P>(p.x, V);
+      Fe<P> XX = fe_mul_call<P>(p.x, p.x);
+      Fe<P> M = fe_add<P>(fe_dbl<P>(XX), XX);
+      acc.X = fe_sub<P>(fe_sub<P>(fe_mul_call<P>(M, M), S), S);
+      acc.Y = fe_sub<P>(fe_mul_call<P>(M, fe_sub<P>(S, acc.X)), fe_mul_call<P>(W, p.y));
+      acc.ZZ = V;
+      acc.ZZZ = W;
+    } else {
+      acc = xyzz_inf<P>();
+    }
+    return;
+  }
+  Fe<P> PP = fe_mul_call<P>(Pd, Pd);
+  Fe<P> PPP = fe_mul_call<P>(Pd, PP);
+  Fe<P> Q = fe_mul_call<P>(acc.X, PP);
+  Fe<P> X3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_mul_call<P>(R, R), PPP), Q), Q);
+  Fe<P> Y3 = fe_sub<P>(fe_mul_call<P>(R, fe_sub<P>(Q, X3)), fe_mul_call<P>(acc.Y, PPP));
+  acc.ZZ = fe_mul_call<P>(acc.ZZ, PP);
+  acc.ZZZ = fe_mul_call<P>(acc.ZZZ, PPP);
+  acc.X = X3;
+  acc.Y = Y3;
+}
+
+// acc += p   (p affine, already known not to be infinity).  The bucket-insertion primitive.
+template <class P, bool CALLS = false>
 ZK_HD void xyzz_madd(Xyzz<P>& acc, const Affine<P>& p) {
+  if (CALLS) { xyzz_madd_calls<P>(acc, p); return; }
   if (xyzz_is_inf<P>(acc)) {
     acc = xyzz_from_affine<P>(p);
     return;

@@ -125,6 +125,21 @@ ZK_HD Fe<P> fe_sqr(const Fe<P>& a) {
   return fe_mul<P>(a, a);
 }
 
+// Out-of-line multiplication: ONE copy of the unrolled product per kernel instead of one per call site.
+// Operands travel in registers (no stack traffic); used where the fully inlined group operation would
+// not fit the instruction cache (k_accumulate: 10 multiplications per insertion).
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Fe<P> fe_mul_call(Fe<P> a, Fe<P> b) {
+  Fe<P> r;
+  mont_mul_limbs<P>(r.l, a.l, b.l);
+  return r;
+}
+#else
+template <class P>
+inline Fe<P> fe_mul_call(Fe<P> a, Fe<P> b) { return fe_mul<P>(a, b); }
+#endif
+
 template <class P>
 ZK_HD Fe<P> fe_add(const Fe<P>& a, const Fe<P>& b) {
   constexpr int L = P::L;

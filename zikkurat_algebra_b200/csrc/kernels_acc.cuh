@@ -4,6 +4,8 @@
 //   lib/cbits/curves/g1/proj/bn128_G1_proj.c:629-643 (Fr Montgomery -> standard conversion)
 #pragma once
 #include "ec_team.cuh"
+#include <cstdlib>
+
 #include "msm_common.cuh"
 
 namespace zk {
@@ -47,8 +49,8 @@ k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int
 // writer); the chunk's first run may continue a run of the previous chunk and goes to heads[t]
 // instead, to be folded in by k_fixup.  Work per thread is exactly `chunk` insertions whatever the
 // scalar distribution, so there is no bucket-size imbalance.
-template <class C>
-__global__ void __launch_bounds__(128)
+template <class C, bool CALLS>
+__global__ void __launch_bounds__(128, C::Fp::L == 8 ? 4 : 3)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const uint32_t* __restrict__ points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
              uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets,
@@ -84,7 +86,7 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
       cur = key;
       acc = inf ? xyzz_inf<P>() : xyzz_from_affine<P>(pt);
     } else if (!inf) {
-      xyzz_madd<P>(acc, pt);
+      xyzz_madd<P, CALLS>(acc, pt);
     }
   }
   if (cur != 0) {
@@ -151,6 +153,16 @@ k_fixup_level(const uint32_t* __restrict__ keys_in, const XyzzMem<typename C::Fp
   if (!last && tm.t == 0) keys_out[t] = head_key;
 }
 
+// Code shape of the insertion: 0 = every multiplication inlined (120 KB of SASS for 12 limbs),
+// 1 = multiplications out of line (fits the instruction cache).  Measured on B200: 12 limbs run 3-5 %
+// faster with 1, 8 limbs 10 % faster with 0 (profiles/r1_notes.md).  Override: $ZKB200_ACC_VARIANT.
+template <class C>
+inline int accumulate_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ZKB200_ACC_VARIANT"); v = e ? atoi(e) : (C::Fp::L > 8 ? 1 : 0); }
+  return v;
+}
+
 template <class C>
 void launch_recode(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int nbits, int c, int W,
                    uint32_t* keys, uint32_t* vals) {
@@ -162,15 +174,20 @@ void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* val
                        int chunk, uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets,
                        XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
   size_t nthreads = (size_t)nseg * chunks_per_seg;
-  k_accumulate<C><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg, NB,
-                                                                    buckets, heads, head_keys);
+  if (accumulate_variant<C>() == 1)
+    k_accumulate<C, true><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg,
+                                                                            NB, buckets, heads, head_keys);
+  else
+    k_accumulate<C, false><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg,
+                                                                             NB, buckets, heads, head_keys);
 }
 template <class C>
 int accumulate_resident_threads() {  // threads of k_accumulate<C> that fit on the whole GPU at once
   int dev = 0, sms = 0, blocks = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C>, 128, 0);
+  if (accumulate_variant<C>() == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C, true>, 128, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C, false>, 128, 0);
   if (blocks < 1) blocks = 1;
   return sms * blocks * 128;
 }

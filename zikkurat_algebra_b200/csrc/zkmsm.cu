@@ -32,22 +32,26 @@ namespace {
 
 enum Buf {
   B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
-  B_U0, B_V0, B_U1, B_V1, B_OUT, B_COUNT
+  B_U0, B_V0, B_U1, B_V1, B_STATE, B_OUT, B_COUNT
 };
 constexpr int N_EV = 9;
 constexpr int MAX_DEV = 16;
 
 struct Stats {
   float ms[9] = {0};
-  int c = 0, W = 0;
+  int c = 0, W = 0, groups = 1;
+  bool have_groups = false;
+  bool group_ran[8] = {false};
   long long insertions = 0;
 };
+constexpr int MAX_GROUPS = 8;
 
 struct DeviceCtx {
   bool ready = false;
   int dev = 0;
-  cudaStream_t s_main = nullptr, s_copy = nullptr;
+  cudaStream_t s_main = nullptr, s_copy = nullptr, s_side = nullptr;
   cudaEvent_t ev[N_EV + 1] = {nullptr};
+  cudaEvent_t gev[6 * 8] = {nullptr};  // per window group: accumulate start/end, fix-up end, reduce start/end, tail end
   cudaEvent_t ev_points = nullptr;
   void* buf[B_COUNT] = {nullptr};
   size_t cap[B_COUNT] = {0};
@@ -108,6 +112,12 @@ DeviceCtx& get_ctx() {
       cx.dev = d;
       CK(cudaStreamCreateWithFlags(&cx.s_main, cudaStreamNonBlocking));
       CK(cudaStreamCreateWithFlags(&cx.s_copy, cudaStreamNonBlocking));
+      {
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&cx.s_side, cudaStreamNonBlocking, greatest));
+      }
+      for (int i = 0; i < 6 * 8; i++) CK(cudaEventCreate(&cx.gev[i]));
       for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
       CK(cudaEventCreateWithFlags(&cx.ev_points, cudaEventDisableTiming));
       cx.ready = true;
@@ -164,10 +174,11 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   const int nbits = mont ? C::Fr::BITS : 64 * nl;
   int c = 0, W = 0;
   CK(cudaEventRecord(cx.ev[0], s));
+  cudaStream_t fin = s;
   if (n == 0) {
-    for (int i = 1; i < N_EV - 1; i++) CK(cudaEventRecord(cx.ev[i], s));
+    for (int i = 1; i <= 4; i++) CK(cudaEventRecord(cx.ev[i], s));
     g_launches++;
-    launch_tail<C>(s, nullptr, nmsm, 0, 0, out_mode, d_out);
+    launch_tail<C>(s, nullptr, nmsm, 0, 0, out_mode, d_out, nullptr, 1, 1);
     CK(cudaGetLastError());
   } else {
     c = window > 0 ? window : pick_window(n, nmsm, nbits);
@@ -220,23 +231,40 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     }
     CK(cudaEventRecord(cx.ev[3], s));
 
-    // ---- bucket accumulation ----
+    // ---- bucket accumulation, reduction and window combination, pipelined over window groups ----
+    // The windows can be processed top-down in G groups ($ZKB200_GROUPS, default 1).  Main stream:
+    // accumulate + head fix-up of group g; side stream (higher priority): bucket reduction of group g and
+    // its share of the Horner chain, meant to run underneath the accumulation of group g-1.  Measured on
+    // B200 (profiles/r1_notes.md) this loses: every small side-stream launch waits for a resident
+    // accumulate CTA to retire, so G = 1 (everything in order on one stream) is the default.
     Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)nseg * NB * sizeof(Mem));
     CK(cudaMemsetAsync(buckets, 0, (size_t)nseg * NB * sizeof(Mem), s));  // ZZ = 0: every bucket starts at infinity
-    // Sorted pairs per thread.  The grid is sized to a whole number of waves of resident threads so
-    // that all SMs drain together (a partial last wave costs a full chunk time): chunk ~ 48 insertions.
+    int G = 1;
+    if (nmsm == 1) {
+      const char* e = getenv("ZKB200_GROUPS");
+      G = e ? atoi(e) : 1;  // measured on B200: >1 loses (side-stream kernels starve behind resident accumulate CTAs)
+      if (G > W) G = W;
+      if (G > MAX_GROUPS) G = MAX_GROUPS;
+      if (G < 1) G = 1;
+    }
+    st.groups = G;
+    const int Wg_max = (W + G - 1) / G;                       // windows per group (the top group may hold fewer)
+    const int segs_max = nmsm == 1 ? Wg_max : nseg;           // segments handled by one group launch
+    static int resident_cache[2] = {0, 0};
+    int& resident = resident_cache[C::Fp::L == 8 ? 0 : 1];
+    if (resident == 0) resident = accumulate_resident_threads<C>();
+    // Sorted pairs per thread: the grid of every group is a whole number of waves of resident threads so
+    // that all SMs drain together (a partial last wave costs a full chunk time); about 48 insertions each.
     int chunk;
     {
       const char* e = getenv("ZKB200_CHUNK");
       if (e && atoi(e) > 0) {
         chunk = atoi(e);
       } else {
-        static int resident_cache[2] = {0, 0};
-        int& resident = resident_cache[C::Fp::L == 8 ? 0 : 1];
-        if (resident == 0) resident = accumulate_resident_threads<C>();
-        double waves = (double)pairs / ((double)resident * 48.0);
+        size_t gpairs = (size_t)segs_max * n;
+        double waves = (double)gpairs / ((double)resident * 48.0);
         size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
-        size_t per_seg_threads = ((size_t)resident * nw) / (size_t)nseg;   // threads available to one segment
+        size_t per_seg_threads = ((size_t)resident * nw) / (size_t)segs_max;  // threads available to one segment
         if (per_seg_threads < 1) per_seg_threads = 1;
         size_t ch = (n + per_seg_threads - 1) / per_seg_threads;
         if (ch < 8) ch = 8;
@@ -245,81 +273,112 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       }
     }
     const uint32_t chunks_per_seg = (uint32_t)((n + chunk - 1) / chunk);
-    const size_t nthreads = (size_t)nseg * chunks_per_seg;
-    Mem* heads = (Mem*)cx.ensure(B_HEADS, nthreads * sizeof(Mem));
-    uint32_t* head_keys = (uint32_t*)cx.ensure(B_HEADKEYS, nthreads * 4);
+    const size_t nthreads_max = (size_t)segs_max * chunks_per_seg;
+    Mem* heads = (Mem*)cx.ensure(B_HEADS, nthreads_max * sizeof(Mem));
+    uint32_t* head_keys = (uint32_t*)cx.ensure(B_HEADKEYS, nthreads_max * 4);
+    const size_t cap2 = (size_t)segs_max * ((chunks_per_seg + FIXUP_FAN - 1) / FIXUP_FAN);
+    Mem* heads2 = (Mem*)cx.ensure(B_HEADS2, cap2 * sizeof(Mem));
+    uint32_t* head_keys2 = (uint32_t*)cx.ensure(B_HEADKEYS2, cap2 * 4);
+    // reduction level plan (same for every group)
+    int log_m1 = 0;
+    if (c - 1 > 0) {
+      log_m1 = ilog2_floor(((size_t)segs_max << (c - 1)) / 65536 + 1);
+      if (log_m1 < 1) log_m1 = 1;
+      if (log_m1 > 5) log_m1 = 5;
+      if (log_m1 > c - 1) log_m1 = c - 1;
+    }
+    const size_t u0_cap = (size_t)segs_max << (c - 1 - log_m1);
+    Mem* Ub[2] = {(Mem*)cx.ensure(B_U0, u0_cap * sizeof(Mem)), (Mem*)cx.ensure(B_U1, (u0_cap / 2 + 1) * sizeof(Mem))};
+    Mem* Vb[2] = {(Mem*)cx.ensure(B_V0, u0_cap * sizeof(Mem)), (Mem*)cx.ensure(B_V1, (u0_cap / 2 + 1) * sizeof(Mem))};
+    Mem* state = (Mem*)cx.ensure(B_STATE, (size_t)nmsm * sizeof(Mem));
+    cudaStream_t side = cx.s_side;
+
     if (ploc == ZKB200_HOST) CK(cudaStreamWaitEvent(s, cx.ev_points, 0));
     CK(cudaEventRecord(cx.ev[4], s));
-    g_launches++;
-    launch_accumulate<C>(s, keys[cur], vals[cur], d_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(cx.ev[5], s));
-    {  // fold the chunk heads into the buckets: log_FAN(chunks_per_seg) tiny levels
-      uint32_t T = chunks_per_seg;
-      size_t cap2 = (size_t)nseg * ((T + FIXUP_FAN - 1) / FIXUP_FAN);
-      Mem* hb[2] = {heads, (Mem*)cx.ensure(B_HEADS2, cap2 * sizeof(Mem))};
-      uint32_t* kb[2] = {head_keys, (uint32_t*)cx.ensure(B_HEADKEYS2, cap2 * 4)};
-      int src = 0;
-      for (;;) {
-        uint32_t T_out = (T + FIXUP_FAN - 1) / FIXUP_FAN;
-        int last = T_out == 1;
-        g_launches++;
-        launch_fixup_level<C>(s, kb[src], hb[src], T, kb[src ^ 1], hb[src ^ 1], T_out, nseg, NB, buckets, last);
-        CK(cudaGetLastError());
-        if (last) break;
-        T = T_out;
-        src ^= 1;
-      }
-    }
-    CK(cudaEventRecord(cx.ev[6], s));
-
-    // ---- bucket reduction by levels ----
-    int logS = c - 1;  // entries per segment = 2^logS
-    int log_m = 0;
-    if (logS > 0) {
-      log_m = ilog2_floor(((size_t)nseg << logS) / 65536 + 1);
-      if (log_m < 1) log_m = 1;
-      if (log_m > 5) log_m = 5;
-      if (log_m > logS) log_m = logS;
-    }
-    size_t total_out = (size_t)nseg << (logS - log_m);
-    Mem* U[2] = {(Mem*)cx.ensure(B_U0, total_out * sizeof(Mem)), nullptr};
-    Mem* V[2] = {(Mem*)cx.ensure(B_V0, total_out * sizeof(Mem)), nullptr};
-    g_launches++;
-    launch_reduce_first<C>(s, buckets, total_out, log_m, U[0], V[0]);
-    CK(cudaGetLastError());
-    logS -= log_m;
-    int log_M = log_m;
-    int lv = 0;
-    if (logS > 0) {
-      size_t nxt = (size_t)nseg << (logS > 3 ? logS - 3 : 0);
-      U[1] = (Mem*)cx.ensure(B_U1, nxt * sizeof(Mem));
-      V[1] = (Mem*)cx.ensure(B_V1, nxt * sizeof(Mem));
-    }
-    while (logS > 0) {
-      int lm = logS > 3 ? 3 : logS;
-      total_out = (size_t)nseg << (logS - lm);
+    bool started = false;
+    for (int g = G - 1; g >= 0; g--) {
+      // segment range of this group (single MSM: windows [w0, w1); batch: everything)
+      int s0 = 0, s1 = nseg;
+      if (nmsm == 1) { s0 = g * Wg_max; s1 = s0 + Wg_max < W ? s0 + Wg_max : W; }
+      if (s1 <= s0) continue;
+      st.group_ran[g] = true;
+      const int gs = s1 - s0;
+      const uint32_t* gk = keys[cur] + (size_t)s0 * n;
+      const uint32_t* gv = vals[cur] + (size_t)s0 * n;
+      Mem* gb = buckets + (size_t)s0 * NB;
+      cudaEvent_t* ge = cx.gev + 6 * g;
+      CK(cudaEventRecord(ge[0], s));
       g_launches++;
-    launch_reduce_next<C>(s, U[lv], V[lv], total_out, lm, log_M, U[lv ^ 1], V[lv ^ 1]);
+      launch_accumulate<C>(s, gk, gv, d_points, n, gs, chunk, chunks_per_seg, NB, gb, heads, head_keys);
       CK(cudaGetLastError());
-      logS -= lm;
-      log_M += lm;
-      lv ^= 1;
+      CK(cudaEventRecord(ge[1], s));
+      {  // fold the chunk heads into the buckets: log_FAN(chunks_per_seg) small levels
+        uint32_t T = chunks_per_seg;
+        Mem* hb[2] = {heads, heads2};
+        uint32_t* kb[2] = {head_keys, head_keys2};
+        int src = 0;
+        for (;;) {
+          uint32_t T_out = (T + FIXUP_FAN - 1) / FIXUP_FAN;
+          int last = T_out == 1;
+          g_launches++;
+          launch_fixup_level<C>(s, kb[src], hb[src], T, kb[src ^ 1], hb[src ^ 1], T_out, gs, NB, gb, last);
+          CK(cudaGetLastError());
+          if (last) break;
+          T = T_out;
+          src ^= 1;
+        }
+      }
+      CK(cudaEventRecord(ge[2], s));
+      // ---- side stream: reduce this group's buckets, then continue the Horner chain ----
+      cudaStream_t r = G > 1 ? side : s;
+      if (G > 1) CK(cudaStreamWaitEvent(r, ge[2], 0));
+      CK(cudaEventRecord(ge[3], r));
+      int logS = c - 1;
+      size_t total_out = (size_t)gs << (logS - log_m1);
+      g_launches++;
+      launch_reduce_first<C>(r, gb, total_out, log_m1, Ub[0], Vb[0]);
+      CK(cudaGetLastError());
+      logS -= log_m1;
+      int log_M = log_m1, lv = 0;
+      while (logS > 0) {
+        int lm = logS > 3 ? 3 : logS;
+        total_out = (size_t)gs << (logS - lm);
+        g_launches++;
+        launch_reduce_next<C>(r, Ub[lv], Vb[lv], total_out, lm, log_M, Ub[lv ^ 1], Vb[lv ^ 1]);
+        CK(cudaGetLastError());
+        logS -= lm;
+        log_M += lm;
+        lv ^= 1;
+      }
+      CK(cudaEventRecord(ge[4], r));
+      g_launches++;
+      launch_tail<C>(r, Ub[lv], nmsm, nmsm == 1 ? gs : W, c, out_mode, d_out, state, !started, g == 0);
+      started = true;
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(ge[5], r));
     }
-    CK(cudaEventRecord(cx.ev[7], s));
-
-    // ---- window combination + output conversion ----
-    g_launches++;
-    launch_tail<C>(s, U[lv], nmsm, W, c, out_mode, d_out);
-    CK(cudaGetLastError());
+    fin = G > 1 ? side : s;
+    st.have_groups = true;
   }
-  CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(cx.ev[8], s));
+  CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, fin));
+  CK(cudaEventRecord(cx.ev[8], fin));
+  CK(cudaStreamSynchronize(fin));
   CK(cudaStreamSynchronize(s));
   if (ploc == ZKB200_HOST && n) CK(cudaStreamSynchronize(cx.s_copy));
   for (int m = 0; m < nmsm; m++)
     memcpy((uint32_t*)out + (size_t)m * out_coords * L, h_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4);
-  for (int i = 0; i < 8; i++) CK(cudaEventElapsedTime(&st.ms[i], cx.ev[i], cx.ev[i + 1]));
+  for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&st.ms[i], cx.ev[i], cx.ev[i + 1]));
+  if (st.have_groups) {
+    for (int g = 0; g < st.groups; g++) {
+      if (!st.group_ran[g]) continue;
+      float t;
+      cudaEvent_t* ge = cx.gev + 6 * g;
+      if (cudaEventElapsedTime(&t, ge[0], ge[1]) == cudaSuccess) st.ms[4] += t; else (void)cudaGetLastError();
+      if (cudaEventElapsedTime(&t, ge[1], ge[2]) == cudaSuccess) st.ms[5] += t; else (void)cudaGetLastError();
+      if (cudaEventElapsedTime(&t, ge[3], ge[4]) == cudaSuccess) st.ms[6] += t; else (void)cudaGetLastError();
+      if (cudaEventElapsedTime(&t, ge[4], ge[5]) == cudaSuccess) st.ms[7] += t; else (void)cudaGetLastError();
+    }
+  }
   CK(cudaEventElapsedTime(&st.ms[8], cx.ev[0], cx.ev[8]));
   cx.stats = st;
 }
