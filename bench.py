@@ -34,6 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PRODUCTS_PER_INSERTION = {"bn128": 1360, "bls12_381": 3000}   # 10 Fp mul x (2L^2 + L), SURVEY.md 8d
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_accumulate launch from an `ncu --set full` capture
+# (profiles/*_ncu_k_accumulate_*.txt), keyed by (curve, log2 n); None where no capture exists.
+NCU_TRAFFIC = {("bls12_381", 20): 1.549326e9 + 0.153258e9}
 METRIC = "G1 MSM throughput"
 UNIT = "points/s"
 
@@ -70,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -256,16 +259,27 @@ def main():
     ppi = PRODUCTS_PER_INSERTION[curve]
     t_acc = acc_ms / args.steps * 1e-3
     achieved = stats["insertions"] * ppi / t_acc                     # products/s on rank 0's GPU
-    peak = zk.imad_peak(0, 4000)
+    probe = zk.imad_peak(0, 4000)
+    props = torch.cuda.get_device_properties(local_rank)
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    # IMAD.WIDE.U32(.X) occupies the FMA-heavy pipe for 4 cycles per warp instruction (ncu: 21.2 % fma issue
+    # rate <-> 80.7 % sm__pipe_fmaheavy_cycles_active, profiles/r1_a_ncu_k_accumulate_*.txt):
+    # peak = SMs x 4 SMSP x 32 lanes / 4 cycles x SM clock sampled during the run
+    peak = props.multi_processor_count * 4 * 32 / 4.0 * sm_mhz * 1e6
     passes = (stats["window"] + 7) // 8
     sort_bytes = stats["insertions"] * 20 * passes
+    traffic = NCU_TRAFFIC.get((curve, logn))
     roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved / 1e9, "peak": peak / 1e9,
                 "unit": "Gproducts/s (32x32->64-bit multiply-adds)", "frac": achieved / peak,
-                "peak_source": "zkb200_imad_peak(kind=0): register-resident mad.lo.cc/madc.hi.cc chains, measured "
-                               "live on this GPU after the timed region; nominal 148 SM x 64 IMAD/clk x 1.965 GHz / 2 = 9300",
+                "peak_source": f"IMAD pipe: {props.multi_processor_count} SM x 4 SMSP x 32 lanes / 4 cycles per IMAD.WIDE x "
+                               f"{sm_mhz:.0f} MHz (SM clock sampled during the timed region); cross-check: ncu "
+                               "sm__pipe_fmaheavy_cycles_active (profiles/), zkb200_imad_peak carry-chain probe on this GPU = "
+                               f"{probe / 1e9:.0f} Gproducts/s",
+                "probe_gproducts": probe / 1e9,
                 "per_launch": {"insertions": stats["insertions"], "products_per_insertion": ppi, "window_c": stats["window"],
-                               "nwindows": stats["nwindows"], "avg_ms": t_acc * 1e3},
-                "traffic": None,
+                               "nwindows": stats["nwindows"], "avg_ms": t_acc * 1e3,
+                               "algorithmic_gather_bytes": stats["insertions"] * (2 * L * 8 + 8)},
+                "traffic": traffic,
                 "secondary_hbm": {"kernel": "radix sort (3 kernels x passes)", "bytes": sort_bytes,
                                   "achieved_gbs": sort_bytes / (sort_ms / args.steps * 1e-3) / 1e9 if sort_ms else None,
                                   "peak_gbs": _measured_peak("hbm_gbs", 6650.0)}}

@@ -104,8 +104,15 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
 // (one thread per segment) everything goes to the buckets.  Depth is log_FAN(T) whatever the scalar
 // distribution (a window holding one single key is the worst case).
 
+// by value for 8 limbs (register ABI), by reference for 12 (see kernels_red.cuh)
 template <class P>
-__device__ __noinline__ void xyzz_add_tm(const Team& tm, Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add_team<P>(tm, a, b); }
+__device__ __noinline__ Xyzz<P> xyzz_add_tmv(Team tm, Xyzz<P> a, Xyzz<P> b) { return xyzz_add_team<P>(tm, a, b); }
+template <class P>
+__device__ __noinline__ void xyzz_add_tmr(const Team& tm, Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add_team<P>(tm, a, b); }
+template <class P>
+__device__ __forceinline__ void xyzz_add_tm(const Team& tm, Xyzz<P>& a, const Xyzz<P>& b) {
+  if (P::L <= 8) a = xyzz_add_tmv<P>(tm, a, b); else xyzz_add_tmr<P>(tm, a, b);
+}
 
 template <class C>
 __global__ void __launch_bounds__(128)

@@ -16,8 +16,8 @@
 
 namespace zk {
 
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;                          // keys per thread
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_ITEMS = 8;                           // keys per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;    // 4096 pairs per CTA
 constexpr int SORT_RADIX = 256;
 

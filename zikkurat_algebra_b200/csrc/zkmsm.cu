@@ -262,7 +262,12 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         chunk = atoi(e);
       } else {
         size_t gpairs = (size_t)segs_max * n;
-        double waves = (double)gpairs / ((double)resident * 48.0);
+        // 48 insertions per thread keep small problems at several waves; big ones take longer chunks
+        // (up to 192) so that fewer chunk heads have to be folded afterwards, still >= 12 waves.
+        double target = (double)gpairs / ((double)resident * 12.0);
+        if (target < 48.0) target = 48.0;
+        if (target > 192.0) target = 192.0;
+        double waves = (double)gpairs / ((double)resident * target);
         size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
         size_t per_seg_threads = ((size_t)resident * nw) / (size_t)segs_max;  // threads available to one segment
         if (per_seg_threads < 1) per_seg_threads = 1;
