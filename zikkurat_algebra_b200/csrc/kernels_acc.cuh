@@ -49,8 +49,8 @@ k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int
 // writer); the chunk's first run may continue a run of the previous chunk and goes to heads[t]
 // instead, to be folded in by k_fixup.  Work per thread is exactly `chunk` insertions whatever the
 // scalar distribution, so there is no bucket-size imbalance.
-template <class C, bool CALLS>
-__global__ void __launch_bounds__(128, C::Fp::L == 8 ? 4 : 3)
+template <class C, bool CALLS, int MINB = (C::Fp::L == 8 ? 4 : 3)>
+__global__ void __launch_bounds__(128, MINB)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const uint32_t* __restrict__ points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
              uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets,
@@ -181,7 +181,10 @@ void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* val
                        int chunk, uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets,
                        XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
   size_t nthreads = (size_t)nseg * chunks_per_seg;
-  if (accumulate_variant<C>() == 1)
+  if (accumulate_variant<C>() == 2)
+    k_accumulate<C, true, 4><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg,
+                                                                               NB, buckets, heads, head_keys);
+  else if (accumulate_variant<C>() == 1)
     k_accumulate<C, true><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg,
                                                                             NB, buckets, heads, head_keys);
   else
@@ -193,7 +196,8 @@ int accumulate_resident_threads() {  // threads of k_accumulate<C> that fit on t
   int dev = 0, sms = 0, blocks = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (accumulate_variant<C>() == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C, true>, 128, 0);
+  if (accumulate_variant<C>() == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C, true, 4>, 128, 0);
+  else if (accumulate_variant<C>() == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C, true>, 128, 0);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_accumulate<C, false>, 128, 0);
   if (blocks < 1) blocks = 1;
   return sms * blocks * 128;
