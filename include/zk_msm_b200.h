@@ -86,6 +86,11 @@ long long zkb200_launch_count(void);
 /* Device used by subsequent calls of the calling process (default: $ZKB200_DEVICE or 0). */
 void zkb200_set_device(int device);
 
+/* Several devices: every host-buffer MSM call is then sharded over them from inside the library (one host
+ * thread per device; contiguous slices of one MSM, or whole MSMs of a batch), the partial points are summed
+ * on devices[0].  count = 0 or 1 restores single-device operation.  Same as $ZKB200_DEVICES="0,1,.."|"all". */
+void zkb200_set_devices(const int *devices, int count);
+
 /* Phase timings (CUDA events, ms) of the most recent zkb200_msm on this thread's device:
  *  [0] h2d scalars  [1] recode  [2] sort  [3] wait for points h2d  [4] accumulate  [5] fixup
  *  [6] reduce  [7] tail + d2h   [8] total on the compute stream.

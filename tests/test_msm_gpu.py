@@ -246,3 +246,29 @@ def test_full_size_properties_bls12_381_2_20(zk):
 def test_imad_probe_runs(zk):
     v = zk.imad_peak(0, 200)
     assert v > 1e11
+
+
+def test_in_library_multi_gpu_sharding(zk):
+    """$ZKB200_DEVICES / zkb200_set_devices: the C-ABI call itself shards over the GPUs of the box (one host
+    thread per device) -- same bytes as the single-device call.  Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    devs = list(range(min(torch.cuda.device_count(), 8)))
+    for curve, logn in (("bn128", 18), ("bls12_381", 17)):
+        n = (1 << logn) + 37
+        pts = refs.chain_points(curve, n)
+        sc = refs.random_scalars(curve, n, seed=logn + 3)
+        single = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_mont_coeff_affine_out", sc, pts)
+        batch_sc = np.stack([refs.random_scalars(curve, 4096, seed=900 + i) for i in range(len(devs) + 1)])
+        batch_single = zk.msm_batch(curve, batch_sc, pts[:4096], mont=True, out="affine")
+        try:
+            zk.set_devices(devs)
+            multi = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_mont_coeff_affine_out", sc, pts)
+            multi_proj = zk.call_reference_symbol(f"{curve}_G1_jac_MSM_mont_coeff_jac_out", sc, pts)
+            batch_multi = zk.msm_batch(curve, batch_sc, pts[:4096], mont=True, out="affine")
+        finally:
+            zk.set_devices([])
+        assert multi.tobytes() == single.tobytes()
+        assert to_affine_cpu(curve, "jac", multi_proj).tobytes() == single.tobytes()
+        assert batch_multi.tobytes() == batch_single.tobytes()

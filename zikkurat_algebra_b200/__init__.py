@@ -20,7 +20,7 @@ import numpy as np
 
 __all__ = [
     "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "call_reference_symbol",
-    "last_stats", "imad_peak", "set_device", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
+    "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -40,7 +40,7 @@ REFERENCE_SYMBOLS = [
     for o in (r, "affine")
 ] + [f"{c}_G1_{r}_MSM_std_coeff_{r}_out_variable" for c in ("bn128", "bls12_381") for r in ("proj", "jac")]
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
-                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count"]
+                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices"]
 
 _U64P = ctypes.POINTER(ctypes.c_uint64)
 _lib: Optional[ctypes.CDLL] = None
@@ -75,6 +75,8 @@ def lib() -> ctypes.CDLL:
         L.zkb200_gen_chain.argtypes = [ctypes.c_int, ctypes.c_ulonglong, ctypes.c_long, _U64P, _U64P, ctypes.c_void_p, ctypes.c_int]
         L.zkb200_gen_chain.restype = None
         L.zkb200_launch_count.restype = ctypes.c_longlong
+        L.zkb200_set_devices.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        L.zkb200_set_devices.restype = None
         for name in REFERENCE_SYMBOLS:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P, ctypes.c_int] + ([ctypes.c_int] if name.endswith("_variable") else [])
@@ -94,6 +96,12 @@ def _ptr(a: np.ndarray):
 
 def set_device(device: int) -> None:
     lib().zkb200_set_device(int(device))
+
+
+def set_devices(devices) -> None:
+    """Shard every subsequent host-buffer call over these GPUs from inside the library ([] = single device)."""
+    arr = (ctypes.c_int * max(1, len(devices)))(*devices)
+    lib().zkb200_set_devices(arr, len(devices))
 
 
 def call_reference_symbol(name: str, scalars: np.ndarray, points: np.ndarray, npoints: Optional[int] = None,

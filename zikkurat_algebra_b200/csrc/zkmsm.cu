@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../include/zk_msm_b200.h"
 #include "msm_common.cuh"
@@ -93,8 +95,8 @@ int current_device_choice() {
   return d;
 }
 
-DeviceCtx& get_ctx() {
-  int d = current_device_choice();
+DeviceCtx& get_ctx(int d = -1) {
+  if (d < 0) d = current_device_choice();
   if (d < 0 || d >= MAX_DEV) { fprintf(stderr, "[zkmsm_b200] fatal: bad device index %d\n", d); abort(); }
   DeviceCtx& cx = g_ctx[d];
   if (!cx.ready) {
@@ -108,6 +110,8 @@ DeviceCtx& get_ctx() {
         abort();
       }
       if (d >= count) { fprintf(stderr, "[zkmsm_b200] fatal: device %d requested, %d visible\n", d, count); abort(); }
+      int prev_dev = -1;
+      if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
       CK(cudaSetDevice(d));
       cx.dev = d;
       CK(cudaStreamCreateWithFlags(&cx.s_main, cudaStreamNonBlocking));
@@ -120,6 +124,7 @@ DeviceCtx& get_ctx() {
       for (int i = 0; i < 6 * 8; i++) CK(cudaEventCreate(&cx.gev[i]));
       for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
       CK(cudaEventCreateWithFlags(&cx.ev_points, cudaEventDisableTiming));
+      if (prev_dev >= 0) cudaSetDevice(prev_dev);
       cx.ready = true;
     }
   }
@@ -388,15 +393,103 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   cx.stats = st;
 }
 
+// ---- devices used by the C-ABI entry points -----------------------------------------------------------
+// $ZKB200_DEVICES = "all" | "0,1,2,3" makes every host-buffer call shard its work over several GPUs of the box
+// from inside the library (one host thread per device), so that the unchanged single-process Haskell caller
+// gets the multi-GPU path too.  Default: the single device of zkb200_set_device / $ZKB200_DEVICE.
+std::mutex g_devlist_mu;
+std::vector<int> g_devlist;
+bool g_devlist_set = false;
+
+std::vector<int> device_list() {
+  std::lock_guard<std::mutex> lk(g_devlist_mu);
+  if (!g_devlist_set) {
+    g_devlist_set = true;
+    const char* e = getenv("ZKB200_DEVICES");
+    if (e && *e) {
+      int count = 0;
+      if (cudaGetDeviceCount(&count) != cudaSuccess) count = 0;
+      if (!strcmp(e, "all")) {
+        for (int i = 0; i < count && i < MAX_DEV; i++) g_devlist.push_back(i);
+      } else {
+        const char* p = e;
+        while (*p) {
+          char* end = nullptr;
+          long v = strtol(p, &end, 10);
+          if (end == p) break;
+          if (v >= 0 && v < count && v < MAX_DEV) g_devlist.push_back((int)v);
+          p = (*end == ',') ? end + 1 : end;
+        }
+      }
+    }
+  }
+  return g_devlist;
+}
+
+template <class C>
+void run_on(int dev, int nmsm, size_t n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc, int nl, int mont,
+            int out_mode, int window, uint64_t* out) {
+  DeviceCtx& cx = get_ctx(dev);
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  run_msm<C>(cx, nmsm, n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
+}
+
+template <class C>
+void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out);
+
+// Sharded execution over several devices (host buffers only).
+//  * one MSM: contiguous slices of both vectors, one XYZZ partial per device, summed on the first device
+//  * a batch over a shared point array: whole MSMs are dealt out to the devices
+template <class C>
+void run_multi(const std::vector<int>& devs, int nmsm, size_t n, const uint64_t* scalars, const uint64_t* points, int nl,
+               int mont, int out_mode, int window, uint64_t* out) {
+  constexpr int L = C::Fp::L;   // u64 words per affine point = 2 coordinates x L/2
+  const int G = (int)devs.size();
+  const int out_coords = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
+  std::vector<std::thread> th;
+  if (nmsm == 1) {
+    std::vector<uint64_t> parts((size_t)G * 4 * (L / 2));
+    for (int g = 0; g < G; g++) {
+      size_t lo = n * (size_t)g / G, hi = n * (size_t)(g + 1) / G;
+      th.emplace_back([=, &parts] {
+        run_on<C>(devs[g], 1, hi - lo, scalars + lo * nl, ZKB200_HOST, points + lo * L, ZKB200_HOST, nl, mont, OUT_XYZZ, window,
+                  parts.data() + (size_t)g * 4 * (L / 2));
+      });
+    }
+    for (auto& t : th) t.join();
+    DeviceCtx& cx = get_ctx(devs[0]);
+    DeviceGuard guard(cx.dev);
+    std::lock_guard<std::mutex> lk(cx.mu);
+    run_sum<C>(cx, G, parts.data(), OUT_XYZZ, out_mode, out);
+  } else {
+    for (int g = 0; g < G; g++) {
+      int lo = (int)((long long)nmsm * g / G), hi = (int)((long long)nmsm * (g + 1) / G);
+      if (hi <= lo) continue;
+      th.emplace_back([=] {
+        run_on<C>(devs[g], hi - lo, n, scalars + (size_t)lo * n * nl, ZKB200_HOST, points, ZKB200_HOST, nl, mont, out_mode, window,
+                  out + (size_t)lo * out_coords * (L / 2));
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+}
+
 void msm_entry(int curve, int nmsm, long n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc, int nl,
                int mont, int out_mode, int window, uint64_t* out) {
   if (n < 0) n = 0;
-  DeviceCtx& cx = get_ctx();
-  DeviceGuard guard(cx.dev);
-  std::lock_guard<std::mutex> lk(cx.mu);
-  if (curve == ZKB200_BN128) run_msm<Bn254>(cx, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
-  else if (curve == ZKB200_BLS12_381) run_msm<Bls12381>(cx, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
-  else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+  if (curve != ZKB200_BN128 && curve != ZKB200_BLS12_381) { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+  std::vector<int> devs = device_list();
+  const bool multi = devs.size() > 1 && sloc == ZKB200_HOST && ploc == ZKB200_HOST && nmsm >= 1 &&
+                     ((nmsm == 1 && (size_t)n >= ((size_t)1 << 16) * devs.size()) || (nmsm >= (int)devs.size()));
+  if (multi) {
+    if (curve == ZKB200_BN128) run_multi<Bn254>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out);
+    else run_multi<Bls12381>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out);
+    return;
+  }
+  int dev = devs.size() == 1 ? devs[0] : -1;
+  if (curve == ZKB200_BN128) run_on<Bn254>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
+  else run_on<Bls12381>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
 }
 
 template <class C>
@@ -499,6 +592,13 @@ void zkb200_sum_points(int curve, int k, const uint64_t* in, int in_mode, int ou
 }
 
 void zkb200_set_device(int device) { g_device.store(device); }
+
+void zkb200_set_devices(const int* devices, int count) {
+  std::lock_guard<std::mutex> lk(g_devlist_mu);
+  g_devlist.clear();
+  for (int i = 0; i < count; i++) if (devices[i] >= 0 && devices[i] < MAX_DEV) g_devlist.push_back(devices[i]);
+  g_devlist_set = true;
+}
 
 long long zkb200_launch_count(void) { return g_launches.load(); }
 
