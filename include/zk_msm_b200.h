@@ -56,6 +56,19 @@ void bn128_G1_jac_MSM_std_coeff_jac_out_variable      (int npoints, const uint64
 void bls12_381_G1_proj_MSM_std_coeff_proj_out_variable(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs, int window_size);
 void bls12_381_G1_jac_MSM_std_coeff_jac_out_variable  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs, int window_size);
 
+/* ---- next row of the scope table: batch conversions, same names and signatures as the
+ * reference (lib/cbits/curves/g1/proj/bn128_G1_proj.h:9-10, .../jac/bn128_G1_jac.h:9-10 and twins).  They feed
+ * Proj.msmProj = msm cs (batchToAffine gs)  (lib/src/ZK/Algebra/Curves/BN128/G1/Proj.hs:222-223).  The
+ * reference performs N separate inversions; here one inversion per 4 points on the GPU.  Bit-identical output. */
+void bn128_G1_proj_batch_to_affine       (int N, const uint64_t *src, uint64_t *tgt);
+void bn128_G1_proj_batch_from_affine     (int N, const uint64_t *src, uint64_t *tgt);
+void bn128_G1_jac_batch_to_affine        (int N, const uint64_t *src, uint64_t *tgt);
+void bn128_G1_jac_batch_from_affine      (int N, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_proj_batch_to_affine   (int N, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_proj_batch_from_affine (int N, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_jac_batch_to_affine    (int N, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_jac_batch_from_affine  (int N, const uint64_t *src, uint64_t *tgt);
+
 /* ---- extensions (not in the reference) -------------------------------------------------------- */
 enum { ZKB200_BN128 = 0, ZKB200_BLS12_381 = 1 };
 enum { ZKB200_OUT_PROJ = 0, ZKB200_OUT_JAC = 1, ZKB200_OUT_AFFINE = 2, ZKB200_OUT_XYZZ = 3 };

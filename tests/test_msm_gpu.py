@@ -272,3 +272,48 @@ def test_in_library_multi_gpu_sharding(zk):
         assert multi.tobytes() == single.tobytes()
         assert to_affine_cpu(curve, "jac", multi_proj).tobytes() == single.tobytes()
         assert batch_multi.tobytes() == batch_single.tobytes()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_batch_conversions_next_row(zk, curve):
+    """<curve>_G1_{proj,jac}_batch_{to,from}_affine, bit-identical to the reference C
+    (which does N separate inversions: bn128_G1_proj.c:158-166)."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    rng = random.Random(77)
+    n = 203
+    aff_pts = pyec.chain_points(cv, n, 11, 13)
+    for k in (0, 5, 100, 202):
+        aff_pts[k] = None
+    lib, pre = cpu_lib()
+    for rep in ("proj", "jac"):
+        recs = []
+        for P in aff_pts:
+            if P is None:
+                z = 0
+                X, Y = (rng.randrange(1, cv.p), rng.randrange(1, cv.p))
+            else:
+                z = rng.randrange(1, cv.p)
+                X = P[0] * (z if rep == "proj" else z * z) % cv.p
+                Y = P[1] * (z if rep == "proj" else z * z * z) % cv.p
+            recs.append(cv.fp_to_bytes(X) + cv.fp_to_bytes(Y) + cv.fp_to_bytes(z))
+        src = np.frombuffer(b"".join(recs), dtype=np.uint64).copy().reshape(n, 3 * L)
+        got = zk.batch_to_affine(curve, src, rep)
+        assert got.tobytes() == cv.points_to_bytes(aff_pts)
+        f = getattr(lib, f"{pre}{curve}_G1_{rep}_to_affine")
+        for i in (0, 1, 5, 77, 202):
+            assert refs.call2(lib, f"{pre}{curve}_G1_{rep}_to_affine", src[i].copy(), 2 * L).tobytes() == got[i].tobytes()
+        # from_affine: exact records, infinity encodings included
+        aff = np.frombuffer(cv.points_to_bytes(aff_pts), dtype=np.uint64).copy().reshape(n, 2 * L)
+        back = zk.batch_from_affine(curve, aff, rep)
+        if refs.have_ref():
+            g = getattr(refs.ref(), f"{curve}_G1_{rep}_batch_from_affine")
+            g.argtypes = [ctypes.c_int, refs.U64P, refs.U64P]
+            g.restype = None
+            want = np.zeros((n, 3 * L), np.uint64)
+            g(n, refs.ptr(aff.ravel()), refs.ptr(want.ravel()))
+            assert back.tobytes() == want.tobytes()
+        assert zk.batch_to_affine(curve, back, rep).tobytes() == aff.tobytes()
+    # a larger round trip through MSM-independent data: 2^16 chain points -> proj -> affine
+    big = refs.chain_points(curve, 1 << 16)
+    assert zk.batch_to_affine(curve, zk.batch_from_affine(curve, big, "jac"), "jac").tobytes() == big.tobytes()

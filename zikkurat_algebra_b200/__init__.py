@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 __all__ = [
-    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "call_reference_symbol",
+    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "call_reference_symbol",
     "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
 ]
 
@@ -39,6 +39,7 @@ REFERENCE_SYMBOLS = [
     for f in ("std", "mont")
     for o in (r, "affine")
 ] + [f"{c}_G1_{r}_MSM_std_coeff_{r}_out_variable" for c in ("bn128", "bls12_381") for r in ("proj", "jac")]
+CONVERT_SYMBOLS = [f"{c}_G1_{r}_batch_{d}_affine" for c in ("bn128", "bls12_381") for r in ("proj", "jac") for d in ("to", "from")]
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
                      "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices"]
 
@@ -77,6 +78,10 @@ def lib() -> ctypes.CDLL:
         L.zkb200_launch_count.restype = ctypes.c_longlong
         L.zkb200_set_devices.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         L.zkb200_set_devices.restype = None
+        for name in CONVERT_SYMBOLS:
+            f = getattr(L, name)
+            f.argtypes = [ctypes.c_int, _U64P, _U64P]
+            f.restype = None
         for name in REFERENCE_SYMBOLS:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P, ctypes.c_int] + ([ctypes.c_int] if name.endswith("_variable") else [])
@@ -161,6 +166,25 @@ def msm_device(curve: str, scalars_ptr: int, points_ptr: int, npoints: int, nmsm
     lib().zkb200_msm(cv["id"], nmsm, npoints, scalars_ptr, DEVICE, points_ptr, DEVICE, expo_nlimbs, int(mont), mode,
                      window, _ptr(res))
     return res
+
+
+def batch_to_affine(curve: str, pts: np.ndarray, repr: str = "proj") -> np.ndarray:
+    """(N, 3L) projective / Jacobian points -> (N, 2L) canonical affine (the reference's batchToAffine)."""
+    a = _as_u64(pts)
+    n = a.shape[0]
+    out = np.zeros((n, 2 * CURVES[curve]["nlimbs_p"]), dtype=np.uint64)
+    if n:
+        getattr(lib(), f"{curve}_G1_{repr}_batch_to_affine")(n, _ptr(a.ravel()), _ptr(out.ravel()))
+    return out
+
+
+def batch_from_affine(curve: str, pts: np.ndarray, repr: str = "proj") -> np.ndarray:
+    a = _as_u64(pts)
+    n = a.shape[0]
+    out = np.zeros((n, 3 * CURVES[curve]["nlimbs_p"]), dtype=np.uint64)
+    if n:
+        getattr(lib(), f"{curve}_G1_{repr}_batch_from_affine")(n, _ptr(a.ravel()), _ptr(out.ravel()))
+    return out
 
 
 def sum_points(curve: str, pts: np.ndarray, in_repr: str = "proj", out: str = "affine") -> np.ndarray:

@@ -185,6 +185,81 @@ k_gen_chain(const uint32_t* __restrict__ p0d, unsigned long long start, size_t n
   else { for (int j = 0; j < 2 * L; j++) o[j] = 0xffffffffu; }
 }
 
+// ---- next row of the scope table: batch conversions -------------------------------
+// <curve>_G1_{proj,jac}_batch_to_affine: the reference does N separate inversions
+// (lib/cbits/curves/g1/proj/bn128_G1_proj.c:158-166 -> :132-144; jac: bn128_G1_jac.c:147-155 -> :120-136).
+// Here every thread converts BATCH consecutive points with ONE inversion (Montgomery's trick); Z = 0 gives
+// the all-0xFF record exactly like the reference.  Output is canonical, hence bit-identical.
+constexpr int TOAFF_BATCH = 4;
+template <class C, bool JAC>
+__global__ void __launch_bounds__(128)
+k_batch_to_affine(const uint32_t* __restrict__ src, size_t n, uint32_t* __restrict__ dst) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t first = t * TOAFF_BATCH;
+  if (first >= n) return;
+  int cnt = (int)((n - first) < (size_t)TOAFF_BATCH ? (n - first) : (size_t)TOAFF_BATCH);
+  Fe<P> z[TOAFF_BATCH], pre[TOAFF_BATCH];
+  Fe<P> acc = fe_one<P>();
+  for (int k = 0; k < cnt; k++) {
+    z[k] = read_fe<P>(src + (first + k) * 3 * L + 2 * L);
+    pre[k] = acc;
+    if (!fe_is_zero<P>(z[k])) acc = fe_mul_call<P>(acc, z[k]);
+  }
+  Fe<P> inv = fe_inv<P>(acc);   // acc is a product of non-zero elements (or one)
+  for (int k = cnt - 1; k >= 0; k--) {
+    uint32_t* o = dst + (first + k) * 2 * L;
+    if (fe_is_zero<P>(z[k])) {
+      for (int i = 0; i < 2 * L; i++) o[i] = 0xffffffffu;
+      continue;
+    }
+    Fe<P> zi = fe_mul_call<P>(inv, pre[k]);
+    inv = fe_mul_call<P>(inv, z[k]);
+    const uint32_t* s = src + (first + k) * 3 * L;
+    Fe<P> X = read_fe<P>(s), Y = read_fe<P>(s + L);
+    if (JAC) {
+      Fe<P> zi2 = fe_mul_call<P>(zi, zi);
+      write_fe<P>(o, fe_mul_call<P>(X, zi2));
+      write_fe<P>(o + L, fe_mul_call<P>(Y, fe_mul_call<P>(zi2, zi)));
+    } else {
+      write_fe<P>(o, fe_mul_call<P>(X, zi));
+      write_fe<P>(o + L, fe_mul_call<P>(Y, zi));
+    }
+  }
+}
+// <curve>_G1_{proj,jac}_batch_from_affine (bn128_G1_proj.c:147-155 -> :120-128; bn128_G1_jac.c:138-145 -> :105-116)
+template <class C, bool JAC>
+__global__ void __launch_bounds__(256)
+k_batch_from_affine(const uint32_t* __restrict__ src, size_t n, uint32_t* __restrict__ dst) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<P> a;
+  const uint32_t* s = src + i * 2 * L;
+  a.x = read_fe<P>(s); a.y = read_fe<P>(s + L);
+  uint32_t* o = dst + i * 3 * L;
+  if (affine_is_inf<P>(a)) {
+    write_fe<P>(o, JAC ? fe_one<P>() : fe_zero<P>());
+    write_fe<P>(o + L, fe_one<P>());
+    write_fe<P>(o + 2 * L, fe_zero<P>());
+  } else {
+    write_fe<P>(o, a.x); write_fe<P>(o + L, a.y); write_fe<P>(o + 2 * L, fe_one<P>());
+  }
+}
+template <class C>
+void launch_batch_to_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac) {
+  size_t threads = (n + TOAFF_BATCH - 1) / TOAFF_BATCH;
+  if (jac) k_batch_to_affine<C, true><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(src, n, dst);
+  else k_batch_to_affine<C, false><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(src, n, dst);
+}
+template <class C>
+void launch_batch_from_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac) {
+  if (jac) k_batch_from_affine<C, true><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, n, dst);
+  else k_batch_from_affine<C, false><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, n, dst);
+}
+
 template <class C>
 void launch_gen_chain(cudaStream_t s, const uint32_t* p0d, unsigned long long start, size_t n, uint32_t* out) {
   k_gen_chain<C><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p0d, start, n, out);
@@ -217,6 +292,8 @@ void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, i
   template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*, XyzzMem<C::Fp>*, int,   \
                                int);                                                                                     \
   template void launch_sum_points<C>(cudaStream_t, const uint32_t*, int, int, int, uint32_t*);                             \
-  template void launch_gen_chain<C>(cudaStream_t, const uint32_t*, unsigned long long, size_t, uint32_t*);
+  template void launch_gen_chain<C>(cudaStream_t, const uint32_t*, unsigned long long, size_t, uint32_t*);               \
+  template void launch_batch_to_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);                         \
+  template void launch_batch_from_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);
 
 }  // namespace zk

@@ -92,6 +92,8 @@ template <class C> void launch_reduce_next(cudaStream_t s, const XyzzMem<typenam
 template <class C> void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int Wg, int c, int mode, uint32_t* out,
                                     XyzzMem<typename C::Fp>* state, int first, int last);
 template <class C> void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out);
+template <class C> void launch_batch_to_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);
+template <class C> void launch_batch_from_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);
 template <class C> void launch_gen_chain(cudaStream_t s, const uint32_t* p0d, unsigned long long start, size_t n, uint32_t* out);
 
 }  // namespace zk

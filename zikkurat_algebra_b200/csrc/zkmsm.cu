@@ -571,6 +571,28 @@ void run_gen_chain(DeviceCtx& cx, unsigned long long start, long n, const uint64
   CK(cudaStreamSynchronize(cx.s_main));
 }
 
+// batch conversions between the reference's representations (host buffers in, host buffers out)
+template <class C>
+void run_convert(int N, const uint64_t* src, uint64_t* tgt, int jac, int to_affine) {
+  constexpr int L = C::Fp::L;
+  if (N <= 0) return;
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  size_t n = (size_t)N;
+  size_t in_bytes = n * (to_affine ? 3 : 2) * L * 4, out_bytes = n * (to_affine ? 2 : 3) * L * 4;
+  uint32_t* d_in = (uint32_t*)cx.ensure(B_POINTS, in_bytes);
+  uint32_t* d_out = (uint32_t*)cx.ensure(B_KEYS0, out_bytes);
+  cudaStream_t s = cx.s_main;
+  CK(cudaMemcpyAsync(d_in, src, in_bytes, cudaMemcpyHostToDevice, s));
+  g_launches++;
+  if (to_affine) launch_batch_to_affine<C>(s, d_in, n, d_out, jac);
+  else launch_batch_from_affine<C>(s, d_in, n, d_out, jac);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(tgt, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+}
+
 }  // namespace
 
 // ---- exported C ABI -----------------------------------------------------------------------------------
@@ -675,6 +697,15 @@ const char* zkb200_version(void) { return "zkmsm_b200 0.1 (sm_100a)"; }
                                                     int ws) {                                                         \
     if (ws < 1 || ws > 64) { fprintf(stderr, "[zkmsm_b200] fatal: window_size %d out of range\n", ws); abort(); }     \
     msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_JAC, ws, t); }
+
+#define ZK_CONVERT_SYMBOLS(NAME, CURVE)                                                                               \
+  void NAME##_G1_proj_batch_to_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE>(N, src, tgt, 0, 1); }   \
+  void NAME##_G1_jac_batch_to_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE>(N, src, tgt, 1, 1); }    \
+  void NAME##_G1_proj_batch_from_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE>(N, src, tgt, 0, 0); } \
+  void NAME##_G1_jac_batch_from_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE>(N, src, tgt, 1, 0); }
+
+ZK_CONVERT_SYMBOLS(bn128, Bn254)
+ZK_CONVERT_SYMBOLS(bls12_381, Bls12381)
 
 ZK_REF_SYMBOLS(bn128, ZKB200_BN128)
 ZK_REF_SYMBOLS(bls12_381, ZKB200_BLS12_381)
