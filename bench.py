@@ -136,8 +136,18 @@ def cpu_reference_arm(curve, logn, steps, warmup, quiet=False):
                        f"({curve}_G1_proj_MSM_mont_coeff_proj_out per shard + proj_add + proj_to_affine)")
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner) write to fd 1, so fd 1
+    is pointed at stderr for the whole run and the saved descriptor is used for the result."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
     args = parse()
+    out = _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -158,7 +168,8 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
         return
 
     import numpy as np
@@ -295,7 +306,8 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_arm(curve, logn, steps=1, warmup=0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     if world > 1:
         dist.destroy_process_group()
 
