@@ -54,6 +54,27 @@ def test_fp_ops(he, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_fp_fused_mul_add(he, curve):
+    """(a*b + c*d) * R^-1 with a single reduction: extreme operands stress the 3p row bound."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    rng = random.Random(21)
+    f = getattr(he, f"he_{curve}_fp_mul2")
+    f.argtypes = [refs.U64P] * 5
+    f.restype = None
+    Rinv = pow(cv.R, -1, cv.p)
+    edge = [0, 1, cv.p - 1, cv.p - 2, (1 << (64 * L - 3)) % cv.p, cv.R % cv.p]
+    quads = [(a, b, c, d) for a in edge for b in edge for c in (0, cv.p - 1) for d in (1, cv.p - 1)]
+    quads += [tuple(rng.randrange(cv.p) for _ in range(4)) for _ in range(3000)]
+    quads += [tuple(cv.p - 1 - rng.randrange(1 << 40) for _ in range(4)) for _ in range(500)]
+    for a, b, c, d in quads:
+        arrs = [_arr(x.to_bytes(8 * L, "little")) for x in (a, b, c, d)]
+        out = np.zeros(L, np.uint64)
+        f(*[refs.ptr(x) for x in arrs], refs.ptr(out))
+        assert int.from_bytes(out.tobytes(), "little") == (a * b + c * d) * Rinv % cv.p
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_fp_mul_matches_oracle_bytes(he, curve):
     L = refs.CURVE_LIMBS[curve]
     cv = pyec.CURVES[curve]

@@ -6,7 +6,8 @@
 //   bn128_G1_proj_add             lib/cbits/curves/g1/proj/bn128_G1_proj.c:272-313
 //   bn128_G1_proj_dbl             lib/cbits/curves/g1/proj/bn128_G1_proj.c:230-263
 //   bn128_G1_jac_madd_jac_aff     lib/cbits/curves/g1/jac/bn128_G1_jac.c:362-422
-// Formulas: EFD "xyzz" madd-2008-s (8M+2S), add-2008-s (12M+2S), dbl-2008-s-1, mdbl-2008-s-1.
+// Formulas: EFD "xyzz" madd-2008-s (8M+2S), add-2008-s (12M+2S), dbl-2008-s-1, mdbl-2008-s-1; the two
+// products of every Y3 share one Montgomery reduction (fe_mul2).
 // The reference treats P+P, P+(-P), inf+P and P+inf explicitly in every addition; so do these
 // routines (the formulas alone would return (0,0,0,0) for P+P).  Intermediate representatives differ
 // from the reference's, which is fine: only canonical affine output is comparable.
@@ -73,7 +74,7 @@ ZK_HD Xyzz<P> xyzz_dbl_affine(const Affine<P>& p) {
   Fe<P> XX = fe_sqr<P>(p.x);
   Fe<P> M = fe_add<P>(fe_dbl<P>(XX), XX);
   r.X = fe_sub<P>(fe_sub<P>(fe_sqr<P>(M), S), S);
-  r.Y = fe_sub<P>(fe_mul<P>(M, fe_sub<P>(S, r.X)), fe_mul<P>(W, p.y));
+  r.Y = fe_mul2<P>(M, fe_sub<P>(S, r.X), W, fe_neg<P>(p.y));   // M*(S - X3) - W*y, one reduction
   r.ZZ = V;
   r.ZZZ = W;
   return r;  // y = 0 (a 2-torsion point) gives ZZ = 0 = infinity, as it must
@@ -91,7 +92,7 @@ ZK_HD Xyzz<P> xyzz_dbl(const Xyzz<P>& a) {
   Fe<P> XX = fe_sqr<P>(a.X);
   Fe<P> M = fe_add<P>(fe_dbl<P>(XX), XX);
   r.X = fe_sub<P>(fe_sub<P>(fe_sqr<P>(M), S), S);
-  r.Y = fe_sub<P>(fe_mul<P>(M, fe_sub<P>(S, r.X)), fe_mul<P>(W, a.Y));
+  r.Y = fe_mul2<P>(M, fe_sub<P>(S, r.X), W, fe_neg<P>(a.Y));   // M*(S - X3) - W*Y1, one reduction
   r.ZZ = fe_mul<P>(V, a.ZZ);
   r.ZZZ = fe_mul<P>(W, a.ZZZ);
   return r;
@@ -115,7 +116,7 @@ ZK_HD void xyzz_madd_calls(Xyzz<P>& acc, const Affine<P>& p) {
       Fe<P> XX = fe_mul_call<P>(p.x, p.x);
       Fe<P> M = fe_add<P>(fe_dbl<P>(XX), XX);
       acc.X = fe_sub<P>(fe_sub<P>(fe_mul_call<P>(M, M), S), S);
-      acc.Y = fe_sub<P>(fe_mul_call<P>(M, fe_sub<P>(S, acc.X)), fe_mul_call<P>(W, p.y));
+      acc.Y = fe_mul2_call<P>(M, fe_sub<P>(S, acc.X), W, fe_neg<P>(p.y));
       acc.ZZ = V;
       acc.ZZZ = W;
     } else {
@@ -127,7 +128,7 @@ ZK_HD void xyzz_madd_calls(Xyzz<P>& acc, const Affine<P>& p) {
   Fe<P> PPP = fe_mul_call<P>(Pd, PP);
   Fe<P> Q = fe_mul_call<P>(acc.X, PP);
   Fe<P> X3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_mul_call<P>(R, R), PPP), Q), Q);
-  Fe<P> Y3 = fe_sub<P>(fe_mul_call<P>(R, fe_sub<P>(Q, X3)), fe_mul_call<P>(acc.Y, PPP));
+  Fe<P> Y3 = fe_mul2_call<P>(R, fe_sub<P>(Q, X3), fe_neg<P>(acc.Y), PPP);   // R*(Q - X3) - Y1*PPP, one reduction
   acc.ZZ = fe_mul_call<P>(acc.ZZ, PP);
   acc.ZZZ = fe_mul_call<P>(acc.ZZZ, PPP);
   acc.X = X3;
@@ -153,7 +154,7 @@ ZK_HD void xyzz_madd(Xyzz<P>& acc, const Affine<P>& p) {
   Fe<P> PPP = fe_mul<P>(Pd, PP);
   Fe<P> Q = fe_mul<P>(acc.X, PP);
   Fe<P> X3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr<P>(R), PPP), Q), Q);
-  Fe<P> Y3 = fe_sub<P>(fe_mul<P>(R, fe_sub<P>(Q, X3)), fe_mul<P>(acc.Y, PPP));
+  Fe<P> Y3 = fe_mul2<P>(R, fe_sub<P>(Q, X3), fe_neg<P>(acc.Y), PPP);   // R*(Q - X3) - Y1*PPP, one reduction
   acc.ZZ = fe_mul<P>(acc.ZZ, PP);
   acc.ZZZ = fe_mul<P>(acc.ZZZ, PPP);
   acc.X = X3;
@@ -180,7 +181,7 @@ ZK_HD Xyzz<P> xyzz_add(const Xyzz<P>& a, const Xyzz<P>& b) {
   Fe<P> PPP = fe_mul<P>(Pd, PP);
   Fe<P> Q = fe_mul<P>(U1, PP);
   r.X = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr<P>(R), PPP), Q), Q);
-  r.Y = fe_sub<P>(fe_mul<P>(R, fe_sub<P>(Q, r.X)), fe_mul<P>(S1, PPP));
+  r.Y = fe_mul2<P>(R, fe_sub<P>(Q, r.X), fe_neg<P>(S1), PPP);   // R*(Q - X3) - S1*PPP, one reduction
   r.ZZ = fe_mul<P>(fe_mul<P>(a.ZZ, b.ZZ), PP);
   r.ZZZ = fe_mul<P>(fe_mul<P>(a.ZZZ, b.ZZZ), PPP);
   return r;
