@@ -317,3 +317,27 @@ def test_batch_conversions_next_row(zk, curve):
     # a larger round trip through MSM-independent data: 2^16 chain points -> proj -> affine
     big = refs.chain_points(curve, 1 << 16)
     assert zk.batch_to_affine(curve, zk.batch_from_affine(curve, big, "jac"), "jac").tobytes() == big.tobytes()
+
+
+def test_concurrent_callers_are_serialised_correctly(zk):
+    """The reference is re-entrant (threading); here concurrent host threads share one device
+    context guarded by a mutex.  Four threads, different inputs, interleaved calls: every result must match."""
+    import threading
+    curve = "bn128"
+    n = 1 << 13
+    pts = refs.chain_points(curve, n)
+    scs = [refs.random_scalars(curve, n, seed=300 + i) for i in range(4)]
+    want = [cpu_affine(curve, sc, pts, "mont").tobytes() for sc in scs]
+    got = [[None] * 3 for _ in range(4)]
+
+    def work(i):
+        for r in range(3):
+            got[i][r] = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_mont_coeff_affine_out", scs[i], pts).tobytes()
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for i in range(4):
+        assert all(g == want[i] for g in got[i])

@@ -136,26 +136,24 @@ k_fixup_level(const uint32_t* __restrict__ keys_in, const XyzzMem<typename C::Fp
   // bucket and the sum is folded in right here, so the upper levels stay empty for ordinary inputs.
   uint32_t prev_key = (lo > 0 && lo < T_in) ? kp[lo - 1] : 0u;
   bool head_open = !last;
-  for (uint32_t e = lo; e <= hi; e++) {
-    uint32_t key = e < hi ? kp[e] : 0xffffffffu;  // sentinel closes the last run
-    if (key == 0) continue;
-    if (key != cur) {
-      if (cur != 0) {
-        if (head_open && cur == prev_key) {
-          if (tm.t == 0) store_xyzz<P>(heads_out + t, acc);
-          head_key = cur;
-          head_open = false;
-        } else {
-          head_open = false;
-          xyzz_add_tm<P>(tm, acc, load_xyzz<P>(bseg + (cur - 1)));
-          if (tm.t == 0) store_xyzz<P>(bseg + (cur - 1), acc);
-        }
-      }
-      cur = key;
-      if (e < hi) acc = load_xyzz<P>(hp + e);
-    } else {
-      xyzz_add_tm<P>(tm, acc, load_xyzz<P>(hp + e));
-    }
+  uint32_t e = lo;
+  for (;;) {
+    uint32_t key = e < hi ? kp[e] : 0xffffffffu;   // sentinel closes the last run
+    if (key == 0) { e++; continue; }
+    const bool same = key == cur;
+    const bool to_head = !same && cur != 0 && head_open && cur == prev_key;
+    const bool to_bucket = !same && cur != 0 && !to_head;
+    // one inlined addition site: either the next partial sum of the open run, or the bucket's current value
+    const XyzzMem<P>* operand = same ? hp + e : (to_bucket ? bseg + (cur - 1) : nullptr);
+    if (operand) acc = xyzz_add_team<P>(tm, acc, load_xyzz<P>(operand));
+    if (same) { e++; continue; }
+    if (to_head) { if (tm.t == 0) store_xyzz<P>(heads_out + t, acc); head_key = cur; }
+    if (to_bucket && tm.t == 0) store_xyzz<P>(bseg + (cur - 1), acc);
+    if (cur != 0) head_open = false;
+    if (e >= hi) break;
+    cur = key;
+    acc = load_xyzz<P>(hp + e);
+    e++;
   }
   if (!last && tm.t == 0) keys_out[t] = head_key;
 }

@@ -56,30 +56,52 @@ k_reduce_first(const XyzzMem<typename C::Fp>* __restrict__ buckets, size_t total
 }
 // Next levels: groups of m entries (t = g*m + i):
 //   U'[g] = sum_i U[t] + M * sum_i i*V[t],   V'[g] = sum_i V[t],   M' = M*m,   M = 2^log_M.
+// One task (= one output entry) is worked on by 16 lanes = 4 teams of 4 lanes.  Three teams run the three
+// chains of the level concurrently -- team 0: run += V_i, team 1: acc += run (one step behind, the run
+// values are handed over through shared memory), team 2: usum += U_i -- so a level is m + 1 dependent
+// additions deep instead of 3m, and the single inlined addition keeps operands in registers.
 template <class C>
 __global__ void __launch_bounds__(128)
 k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typename C::Fp>* __restrict__ Vin,
               size_t total_out, int log_m, int log_M, XyzzMem<typename C::Fp>* __restrict__ Uout,
               XyzzMem<typename C::Fp>* __restrict__ Vout) {
   using P = typename C::Fp;
-  size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;  // one 4-lane team per output entry
+  __shared__ XyzzMem<P> hand[128 / 16][2];   // per task: double-buffered hand-over slot
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   if (g >= total_out) return;
-  Team tm;
+  const Team tm;
+  const int lane = threadIdx.x & 31;
+  const int q = (lane >> 2) & 3;                          // team within the task
+  const unsigned gmask = 0xFFFFu << (lane & 16);          // the 16 lanes of this task
+  XyzzMem<P>* slot = hand[(threadIdx.x >> 4)];
+  const int m = 1 << log_m;
   const XyzzMem<P>* u = Uin + (g << log_m);
   const XyzzMem<P>* v = Vin + (g << log_m);
-  Xyzz<P> run = xyzz_inf<P>(), acc = xyzz_inf<P>(), usum = xyzz_inf<P>();
-  for (int i = (1 << log_m) - 1; i >= 1; i--) {
-    xyzz_add_tm<P>(tm, run, load_xyzz<P>(v + i));
-    xyzz_add_tm<P>(tm, acc, run);
-    xyzz_add_tm<P>(tm, usum, load_xyzz<P>(u + i));
+  Xyzz<P> X = xyzz_inf<P>();                              // this team's chain value
+  for (int s = 0; s <= m; s++) {
+    Xyzz<P> B = xyzz_inf<P>();
+    if (s < m) {
+      const int i = m - 1 - s;
+      if (q == 0) B = load_xyzz<P>(v + i);
+      else if (q == 1) { if (s >= 1) B = load_xyzz<P>(&slot[(s - 1) & 1]); }
+      else if (q == 2) B = load_xyzz<P>(u + i);
+    } else {
+      // last step: team 1 scales its sum by M = 2^log_M and hands it to team 2, which adds it to usum
+      if (q == 1) {
+#pragma unroll 1
+        for (int d = 0; d < log_M; d++) X = xyzz_dbl_team<P>(tm, X);
+        if (tm.t == 0) store_xyzz<P>(&slot[0], X);
+      }
+      __syncwarp(gmask);
+      if (q == 2) B = load_xyzz<P>(&slot[0]);
+    }
+    X = xyzz_add_team<P>(tm, X, B);                       // the only addition site; B = infinity is a no-op
+    if (s < m && q == 0 && tm.t == 0) store_xyzz<P>(&slot[s & 1], X);
+    __syncwarp(gmask);
   }
-  xyzz_add_tm<P>(tm, run, load_xyzz<P>(v));
-  xyzz_add_tm<P>(tm, usum, load_xyzz<P>(u));
-  for (int d = 0; d < log_M; d++) xyzz_dbl_tm<P>(tm, acc);
-  xyzz_add_tm<P>(tm, usum, acc);
   if (tm.t == 0) {
-    store_xyzz<P>(Uout + g, usum);
-    store_xyzz<P>(Vout + g, run);
+    if (q == 2) store_xyzz<P>(Uout + g, X);
+    if (q == 0) store_xyzz<P>(Vout + g, X);
   }
 }
 
@@ -273,7 +295,7 @@ void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets,
 template <class C>
 void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin, size_t total_out,
                         int log_m, int log_M, XyzzMem<typename C::Fp>* Uout, XyzzMem<typename C::Fp>* Vout) {
-  k_reduce_next<C><<<(unsigned)((total_out * 4 + 127) / 128), 128, 0, s>>>(Uin, Vin, total_out, log_m, log_M, Uout, Vout);
+  k_reduce_next<C><<<(unsigned)((total_out * 16 + 127) / 128), 128, 0, s>>>(Uin, Vin, total_out, log_m, log_M, Uout, Vout);
 }
 template <class C>
 void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int Wg, int c, int mode, uint32_t* out,
