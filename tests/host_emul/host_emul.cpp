@@ -51,6 +51,7 @@ static Xyzz<P> sum_list(long n, const uint64_t* pts, const uint8_t* neg) {
     st<C::Fp>(t, fe_mul<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b))); }                                                  \
   extern "C" void he_##NAME##_fp_mul2(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* t) { \
     st<C::Fp>(t, fe_mul2<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b), ld<C::Fp>(c), ld<C::Fp>(d))); }                       \
+  extern "C" void he_##NAME##_fp_sqr(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_sqr<C::Fp>(ld<C::Fp>(a))); }  \
   extern "C" void he_##NAME##_fp_add(const uint64_t* a, const uint64_t* b, uint64_t* t) {                       \
     st<C::Fp>(t, fe_add<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b))); }                                                  \
   extern "C" void he_##NAME##_fp_sub(const uint64_t* a, const uint64_t* b, uint64_t* t) {                       \

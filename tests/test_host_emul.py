@@ -54,6 +54,28 @@ def test_fp_ops(he, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_fp_dedicated_squaring(he, curve):
+    """mont_sqr_limbs (half the cross products, doubled multiplicand) against Python ints and fe_mul(a, a);
+    operands with set top bits in every limb stress the carried-bit handling of the doubled limbs."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    rng = random.Random(33)
+    Rinv = pow(cv.R, -1, cv.p)
+    vals = [0, 1, 2, cv.p - 1, cv.p - 2, (cv.p - 1) // 2, cv.R % cv.p]
+    vals += [int.from_bytes(bytes([0x80, 0, 0, 0x80] * (2 * L)), "little") % cv.p,
+             int.from_bytes(bytes([0xff, 0xff, 0xff, 0xff, 0, 0, 0, 0x80] * L), "little") % cv.p,
+             int.from_bytes(bytes([0, 0, 0, 0x80] * (2 * L)), "little") % cv.p]
+    vals += [rng.randrange(cv.p) for _ in range(5000)]
+    vals += [cv.p - 1 - rng.randrange(1 << 70) for _ in range(300)]
+    vals += [rng.randrange(1 << 70) for _ in range(300)]
+    for a in vals:
+        A = _arr(a.to_bytes(8 * L, "little"))
+        got = refs.call2(he, f"he_{curve}_fp_sqr", A, L)
+        assert int.from_bytes(got.tobytes(), "little") == a * a * Rinv % cv.p, hex(a)
+        assert got.tobytes() == refs.call3(he, f"he_{curve}_fp_mul", A, A, L).tobytes()
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_fp_fused_mul_add(he, curve):
     """(a*b + c*d) * R^-1 with a single reduction: extreme operands stress the 3p row bound."""
     cv = pyec.CURVES[curve]

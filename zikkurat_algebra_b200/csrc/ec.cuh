@@ -110,12 +110,12 @@ ZK_HD void xyzz_madd_calls(Xyzz<P>& acc, const Affine<P>& p) {
   if (fe_is_zero<P>(Pd)) {
     if (fe_is_zero<P>(R)) {  // same point: double (mdbl-2008-s-1)
       Fe<P> U = fe_dbl<P>(p.y);
-      Fe<P> V = fe_mul_call<P>(U, U);
+      Fe<P> V = fe_sqr_call<P>(U);
       Fe<P> W = fe_mul_call<P>(U, V);
       Fe<P> S = fe_mul_call<P>(p.x, V);
-      Fe<P> XX = fe_mul_call<P>(p.x, p.x);
+      Fe<P> XX = fe_sqr_call<P>(p.x);
       Fe<P> M = fe_add<P>(fe_dbl<P>(XX), XX);
-      acc.X = fe_sub<P>(fe_sub<P>(fe_mul_call<P>(M, M), S), S);
+      acc.X = fe_sub<P>(fe_sub<P>(fe_sqr_call<P>(M), S), S);
       acc.Y = fe_mul2_call<P>(M, fe_sub<P>(S, acc.X), W, fe_neg<P>(p.y));
       acc.ZZ = V;
       acc.ZZZ = W;
@@ -124,10 +124,10 @@ ZK_HD void xyzz_madd_calls(Xyzz<P>& acc, const Affine<P>& p) {
     }
     return;
   }
-  Fe<P> PP = fe_mul_call<P>(Pd, Pd);
+  Fe<P> PP = fe_sqr_call<P>(Pd);
   Fe<P> PPP = fe_mul_call<P>(Pd, PP);
   Fe<P> Q = fe_mul_call<P>(acc.X, PP);
-  Fe<P> X3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_mul_call<P>(R, R), PPP), Q), Q);
+  Fe<P> X3 = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr_call<P>(R), PPP), Q), Q);
   Fe<P> Y3 = fe_mul2_call<P>(R, fe_sub<P>(Q, X3), fe_neg<P>(acc.Y), PPP);   // R*(Q - X3) - Y1*PPP, one reduction
   acc.ZZ = fe_mul_call<P>(acc.ZZ, PP);
   acc.ZZZ = fe_mul_call<P>(acc.ZZZ, PPP);

@@ -54,7 +54,7 @@ ZK_D Xyzz<P> xyzz_dbl_team(const Team& tm, const Xyzz<P>& a) {
   Fe<P> U = fe_dbl<P>(a.Y);
   // round 1: V = U^2, XX = X^2
   Fe<P> x = team_sel<P>(tm.t, U, a.X, U, a.X);
-  Fe<P> pr = fe_mul<P>(x, x);
+  Fe<P> pr = fe_sqr<P>(x);
   Fe<P> V = team_get<P>(tm, pr, 0), XX = team_get<P>(tm, pr, 1);
   Fe<P> M = fe_add<P>(fe_dbl<P>(XX), XX);
   // round 2: W = U*V, S = X*V, MM = M^2, ZZ3 = V*ZZ

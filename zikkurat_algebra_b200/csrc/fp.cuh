@@ -175,9 +175,87 @@ ZK_HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
   mont_mul_limbs<P>(r.l, a.l, b.l);
   return r;
 }
+// Montgomery squaring.  Same row structure as mont_mul_limbs, but row i only adds
+//   a_i * ( a_i*2^(32i) + 2*sum_{j>i} a_j*2^(32j) )
+// i.e. L-i products instead of L (the cross terms a_i*a_j are taken once, doubled): L(L+1)/2 + L^2 + L
+// products (108 | 234) instead of 2L^2 + L (136 | 300).  The doubled multiplicand 2a is precomputed as
+// 32-bit limbs d_j = (a_j<<1)|(a_{j-1}>>31); the limb right above the diagonal must not contain the bit
+// carried up from a_i, hence d_{i+1} & ~1.  a < p < 2^(32L-2), so 2a has no limb L.
+// Where a row has no product the chain still has to carry (and, for the accumulator that is shifted down
+// two limbs per row, move) the limb: addc.cc with 0 takes the place of madc.  Row bound as for
+// mont_mul2_limbs: each row adds a_i*W + m*p with W <= 2a < 2p, T stays below 2^(32(L+1)) because 3p < 2^(32L).
+template <class P>
+ZK_HD void mont_sqr_limbs(uint32_t* r, const uint32_t* a) {
+  constexpr int L = P::L;
+  uint32_t A[L], B[L], d[L];
+  d[0] = a[0] << 1;  // unused as a multiplicand (row 0 uses a_0 itself), kept for uniform indexing
+#pragma unroll
+  for (int j = 1; j < L; j++) d[j] = (a[j] << 1) | (a[j - 1] >> 31);
+  // multiplicand limb j of row i (j >= i):  a_i on the diagonal, d_{i+1} without its carried-in bit, d_j above
+#define ZK_SQR_W(i, j) ((j) == (i) ? a[(j)] : ((j) == (i) + 1 ? (d[(j)] & 0xfffffffeu) : d[(j)]))
+  // ---- row 0: full row ----
+#pragma unroll
+  for (int j = 0; j < L; j += 2) {
+    A[j] = mul_lo(ZK_SQR_W(0, j), a[0]);
+    A[j + 1] = mul_hi(ZK_SQR_W(0, j), a[0]);
+    B[j] = mul_lo(ZK_SQR_W(0, j + 1), a[0]);
+    B[j + 1] = mul_hi(ZK_SQR_W(0, j + 1), a[0]);
+  }
+  {
+    uint32_t m = mul_lo(A[0], P::INV);
+    cmad_row_const<L>(B, ModRow<P, 1>(), m);
+    cmad_row_const<L>(A, ModRow<P, 0>(), m);
+    B[L - 1] = addc(B[L - 1], 0u);
+  }
+#pragma unroll
+  for (int i = 1; i < L; i++) {
+    uint32_t* E = (i & 1) ? B : A;
+    uint32_t* O = (i & 1) ? A : B;
+    E[0] = add_cc(E[0], O[1]);
+    // odd positions t = j + 1 (pairs (t, t+1) live in O[j], O[j+1] after the two-limb shift)
+#pragma unroll
+    for (int j = 0; j < L - 2; j += 2) {
+      if (j + 1 >= i) {
+        O[j] = madc_lo_cc(ZK_SQR_W(i, j + 1), a[i], O[j + 2]);
+        O[j + 1] = madc_hi_cc(ZK_SQR_W(i, j + 1), a[i], O[j + 3]);
+      } else {
+        O[j] = addc_cc(O[j + 2], 0u);
+        O[j + 1] = addc_cc(O[j + 3], 0u);
+      }
+    }
+    O[L - 2] = madc_lo_cc(ZK_SQR_W(i, L - 1), a[i], 0u);   // position L-1 >= i always
+    O[L - 1] = madc_hi(ZK_SQR_W(i, L - 1), a[i], 0u);
+    // even positions t = j >= i
+    bool started = false;
+#pragma unroll
+    for (int j = 0; j < L; j += 2) {
+      if (j >= i) {
+        E[j] = started ? madc_lo_cc(ZK_SQR_W(i, j), a[i], E[j]) : mad_lo_cc(ZK_SQR_W(i, j), a[i], E[j]);
+        E[j + 1] = madc_hi_cc(ZK_SQR_W(i, j), a[i], E[j + 1]);
+        started = true;
+      }
+    }
+    if (started) O[L - 1] = addc(O[L - 1], 0u);
+    uint32_t m = mul_lo(E[0], P::INV);
+    cmad_row_const<L>(O, ModRow<P, 1>(), m);
+    cmad_row_const<L>(E, ModRow<P, 0>(), m);
+    O[L - 1] = addc(O[L - 1], 0u);
+  }
+#undef ZK_SQR_W
+  uint32_t* E = ((L - 1) & 1) ? B : A;
+  uint32_t* O = ((L - 1) & 1) ? A : B;
+  r[0] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 1; k < L - 1; k++) r[k] = addc_cc(E[k + 1], O[k]);
+  r[L - 1] = addc(O[L - 1], 0u);
+  final_sub<P>(r);
+}
+
 template <class P>
 ZK_HD Fe<P> fe_sqr(const Fe<P>& a) {
-  return fe_mul<P>(a, a);
+  Fe<P> r;
+  mont_sqr_limbs<P>(r.l, a.l);
+  return r;
 }
 
 // Out-of-line multiplication: ONE copy of the unrolled product per kernel instead of one per call site.
@@ -191,6 +269,12 @@ __device__ __noinline__ Fe<P> fe_mul_call(Fe<P> a, Fe<P> b) {
   return r;
 }
 template <class P>
+__device__ __noinline__ Fe<P> fe_sqr_call(Fe<P> a) {
+  Fe<P> r;
+  mont_sqr_limbs<P>(r.l, a.l);
+  return r;
+}
+template <class P>
 __device__ __noinline__ Fe<P> fe_mul2_call(Fe<P> a, Fe<P> b, Fe<P> c, Fe<P> d) {
   Fe<P> r;
   mont_mul2_limbs<P>(r.l, a.l, b.l, c.l, d.l);
@@ -199,6 +283,8 @@ __device__ __noinline__ Fe<P> fe_mul2_call(Fe<P> a, Fe<P> b, Fe<P> c, Fe<P> d) {
 #else
 template <class P>
 inline Fe<P> fe_mul_call(Fe<P> a, Fe<P> b) { return fe_mul<P>(a, b); }
+template <class P>
+inline Fe<P> fe_sqr_call(Fe<P> a) { return fe_sqr<P>(a); }
 template <class P>
 inline Fe<P> fe_mul2_call(Fe<P> a, Fe<P> b, Fe<P> c, Fe<P> d) {
   Fe<P> r;
