@@ -34,6 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PRODUCTS_PER_INSERTION = {"bn128": 1360, "bls12_381": 3000}   # 10 Fp mul x (2L^2 + L), SURVEY.md 8d
+# what k_accumulate really executes per insertion: 6 mul + 2 dedicated squarings + 1 fused (a*b + c*d):
+# 6(2L^2+L) + 2(L(L+1)/2 + L^2 + L) + (3L^2 + L)
+EXECUTED_PER_INSERTION = {"bn128": 6 * 136 + 2 * 108 + 200, "bls12_381": 6 * 300 + 2 * 234 + 444}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_accumulate launch from an `ncu --set full` capture
 # (profiles/*_ncu_k_accumulate_*.txt), keyed by (curve, log2 n); None where no capture exists.
 NCU_TRAFFIC = {("bls12_381", 20): 1.549326e9 + 0.153258e9}
@@ -287,6 +290,11 @@ def main():
                                "sm__pipe_fmaheavy_cycles_active (profiles/), zkb200_imad_peak carry-chain probe on this GPU = "
                                f"{probe / 1e9:.0f} Gproducts/s",
                 "probe_gproducts": probe / 1e9,
+                "executed": {"products_per_insertion": EXECUTED_PER_INSERTION[curve],
+                             "gproducts_per_s": stats["insertions"] * EXECUTED_PER_INSERTION[curve] / t_acc / 1e9,
+                             "frac_of_pipe_peak": stats["insertions"] * EXECUTED_PER_INSERTION[curve] / t_acc / peak,
+                             "note": "achieved/frac use SURVEY.md 8d's algorithmic 10 Fp mul per insertion; the kernel "
+                                     "executes fewer products (fused Y3 reduction, dedicated squarings)"},
                 "per_launch": {"insertions": stats["insertions"], "products_per_insertion": ppi, "window_c": stats["window"],
                                "nwindows": stats["nwindows"], "avg_ms": t_acc * 1e3,
                                "algorithmic_gather_bytes": stats["insertions"] * (2 * L * 8 + 8)},
