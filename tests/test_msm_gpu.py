@@ -341,3 +341,26 @@ def test_concurrent_callers_are_serialised_correctly(zk):
         t.join()
     for i in range(4):
         assert all(g == want[i] for g in got[i])
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_input_slices_give_identical_bytes(zk, curve):
+    """$ZKB200_SLICES: host inputs cut into K slices that are transferred / sorted / accumulated one after the
+    other into K bucket arrays (H2D overlap).  Any K must give the same bytes, including ragged n and n < K."""
+    pts_all = refs.chain_points(curve, 5003)
+    old = os.environ.get("ZKB200_SLICES")
+    try:
+        for n in (1, 2, 3, 7, 1000, 5003):
+            pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=n, reduce=False)
+            os.environ["ZKB200_SLICES"] = "1"
+            want = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
+            assert want.tobytes() == cpu_affine(curve, sc, pts).tobytes()
+            for K in (2, 3, 8):
+                os.environ["ZKB200_SLICES"] = str(K)
+                got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
+                assert got.tobytes() == want.tobytes(), (n, K)
+    finally:
+        if old is None:
+            os.environ.pop("ZKB200_SLICES", None)
+        else:
+            os.environ["ZKB200_SLICES"] = old

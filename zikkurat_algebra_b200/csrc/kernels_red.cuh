@@ -38,17 +38,20 @@ __device__ __forceinline__ void xyzz_dbl_tm(const Team& tm, Xyzz<P>& a) {
 // ---- K5: bucket reduction  sum_b (b+1) * B[b]  by levels ------------------------------------------------
 // Invariant after every level:  R_seg = sum_t ( U[t] + M * t * V[t] ),  t = 0..S-1.
 // Level 1 reads the buckets (U = V = B, M = 1, weights t+1) with the classic running sum over m buckets.
+// With K input slices (H2D overlap, see run_msm) there are K bucket arrays `slice_stride` apart; their
+// sum is taken on the fly: run += B_0[i] + ... + B_{K-1}[i] through the same addition site.
 template <class C>
 __global__ void __launch_bounds__(128)
-k_reduce_first(const XyzzMem<typename C::Fp>* __restrict__ buckets, size_t total_out, int log_m,
-               XyzzMem<typename C::Fp>* __restrict__ U, XyzzMem<typename C::Fp>* __restrict__ V) {
+k_reduce_first(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices, size_t slice_stride, size_t total_out,
+               int log_m, XyzzMem<typename C::Fp>* __restrict__ U, XyzzMem<typename C::Fp>* __restrict__ V) {
   using P = typename C::Fp;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total_out) return;
   const XyzzMem<P>* b = buckets + (t << log_m);
   Xyzz<P> run = xyzz_inf<P>(), acc = xyzz_inf<P>();
   for (int i = (1 << log_m) - 1; i >= 0; i--) {
-    run = xyzz_add<P>(run, load_xyzz<P>(b + i));
+#pragma unroll 1
+    for (int k = 0; k < nslices; k++) run = xyzz_add<P>(run, load_xyzz<P>(b + (size_t)k * slice_stride + i));
     acc = xyzz_add<P>(acc, run);
   }
   store_xyzz<P>(U + t, acc);
@@ -288,9 +291,9 @@ void launch_gen_chain(cudaStream_t s, const uint32_t* p0d, unsigned long long st
 }
 
 template <class C>
-void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, size_t total_out, int log_m,
-                         XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V) {
-  k_reduce_first<C><<<(unsigned)((total_out + 127) / 128), 128, 0, s>>>(buckets, total_out, log_m, U, V);
+void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, int nslices, size_t slice_stride, size_t total_out,
+                         int log_m, XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V) {
+  k_reduce_first<C><<<(unsigned)((total_out + 127) / 128), 128, 0, s>>>(buckets, nslices, slice_stride, total_out, log_m, U, V);
 }
 template <class C>
 void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin, size_t total_out,
@@ -308,7 +311,8 @@ void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, i
 }
 
 #define ZK_INSTANTIATE_RED(C)                                                                                             \
-  template void launch_reduce_first<C>(cudaStream_t, const XyzzMem<C::Fp>*, size_t, int, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*); \
+  template void launch_reduce_first<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, size_t, size_t, int, XyzzMem<C::Fp>*,     \
+                                       XyzzMem<C::Fp>*);                                                                  \
   template void launch_reduce_next<C>(cudaStream_t, const XyzzMem<C::Fp>*, const XyzzMem<C::Fp>*, size_t, int, int,        \
                                       XyzzMem<C::Fp>*, XyzzMem<C::Fp>*);                                                   \
   template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*, XyzzMem<C::Fp>*, int,   \

@@ -46,15 +46,15 @@ struct Stats {
   bool group_ran[8] = {false};
   long long insertions = 0;
 };
-constexpr int MAX_GROUPS = 8;
+constexpr int MAX_SLICES = 8;
 
 struct DeviceCtx {
   bool ready = false;
   int dev = 0;
   cudaStream_t s_main = nullptr, s_copy = nullptr, s_side = nullptr;
   cudaEvent_t ev[N_EV + 1] = {nullptr};
-  cudaEvent_t gev[6 * 8] = {nullptr};  // per window group: accumulate start/end, fix-up end, reduce start/end, tail end
-  cudaEvent_t ev_points = nullptr;
+  cudaEvent_t gev[6 * 8] = {nullptr};  // per input slice: accumulate start/end, fix-up end, recode start, sort end, recode end
+  cudaEvent_t ev_sc[8] = {nullptr}, ev_pt[8] = {nullptr};   // per input slice: scalars / points have arrived
   void* buf[B_COUNT] = {nullptr};
   size_t cap[B_COUNT] = {0};
   uint32_t* h_out = nullptr;  // pinned staging for results
@@ -123,7 +123,10 @@ DeviceCtx& get_ctx(int d = -1) {
       }
       for (int i = 0; i < 6 * 8; i++) CK(cudaEventCreate(&cx.gev[i]));
       for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
-      CK(cudaEventCreateWithFlags(&cx.ev_points, cudaEventDisableTiming));
+      for (int i = 0; i < 8; i++) {
+        CK(cudaEventCreateWithFlags(&cx.ev_sc[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&cx.ev_pt[i], cudaEventDisableTiming));
+      }
       if (prev_dev >= 0) cudaSetDevice(prev_dev);
       cx.ready = true;
     }
@@ -177,11 +180,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   uint32_t* h_out = cx.ensure_host((size_t)nmsm * 4 * L * 4);
 
   const int nbits = mont ? C::Fr::BITS : 64 * nl;
-  int c = 0, W = 0;
+  int c = 0, W = 0, K = 1;
   CK(cudaEventRecord(cx.ev[0], s));
-  cudaStream_t fin = s;
   if (n == 0) {
-    for (int i = 1; i <= 4; i++) CK(cudaEventRecord(cx.ev[i], s));
     g_launches++;
     launch_tail<C>(s, nullptr, nmsm, 0, 0, out_mode, d_out, nullptr, 1, 1);
     CK(cudaGetLastError());
@@ -192,138 +193,122 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     W = signed_windows(nbits, c);
     const uint32_t NB = 1u << (c - 1);
     const int nseg = nmsm * W;
-    const size_t pairs = (size_t)nseg * n;
-    st.c = c; st.W = W; st.insertions = (long long)pairs;
+    st.c = c; st.W = W; st.insertions = (long long)nseg * (long long)n;
 
-    // ---- scalars -> device, recode ----
+    // ---- point slices -----------------------------------------------------------------------------------
+    // With host buffers the input vectors are cut into K contiguous slices that go through
+    // H2D -> recode -> sort -> accumulate one after the other, each into its OWN bucket array (the K arrays
+    // are summed on the fly by the first reduction level), so that the PCIe transfer of slice k+1 runs under
+    // the accumulation of slice k instead of in front of everything.  Costs one extra bucket addition per
+    // bucket and slice in k_reduce_first.  (Adding into shared buckets inside k_accumulate was tried and
+    // loses: the rare per-run addition diverges and is paid by the whole warp on almost every step.)
+    if (nmsm == 1 && sloc == ZKB200_HOST && ploc == ZKB200_HOST) {
+      const char* e = getenv("ZKB200_SLICES");
+      K = e ? atoi(e) : (n >= ((size_t)1 << 19) ? 2 : 1);   // measured: 2 slices -4 % (2^20) .. -14 % (2^24) end to end
+      if (K > MAX_SLICES) K = MAX_SLICES;
+      if (K < 1) K = 1;
+      if ((size_t)K > n) K = 1;
+    }
+    st.groups = K;
+    size_t lo[MAX_SLICES + 1];
+    size_t nmax = 0;
+    for (int k = 0; k <= K; k++) lo[k] = (n * (size_t)k / K) & ~(size_t)3;   // multiples of 4 keep 16-byte alignment
+    lo[K] = n;
+    for (int k = 0; k < K; k++) if (lo[k + 1] - lo[k] > nmax) nmax = lo[k + 1] - lo[k];
+
+    // ---- inputs -> device: all copies are queued now, in the order they are consumed ----
     const uint64_t* d_scalars = scalars;
-    if (sloc == ZKB200_HOST) {
-      size_t bytes = (size_t)nmsm * n * nl * 8;
-      void* p = cx.ensure(B_SCALARS, bytes);
-      CK(cudaMemcpyAsync(p, scalars, bytes, cudaMemcpyHostToDevice, s));
-      d_scalars = (const uint64_t*)p;
-    }
-    CK(cudaEventRecord(cx.ev[1], s));
-    uint32_t* keys[2] = {(uint32_t*)cx.ensure(B_KEYS0, pairs * 4), (uint32_t*)cx.ensure(B_KEYS1, pairs * 4)};
-    uint32_t* vals[2] = {(uint32_t*)cx.ensure(B_VALS0, pairs * 4), (uint32_t*)cx.ensure(B_VALS1, pairs * 4)};
-    {
-      g_launches++;
-    launch_recode<C>(s, d_scalars, nl, n, nmsm, mont, nbits, c, W, keys[0], vals[0]);
-      CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(cx.ev[2], s));
-
-    // ---- points -> device on the copy stream (overlaps recode + sort) ----
     const uint32_t* d_points = (const uint32_t*)points;
-    if (ploc == ZKB200_HOST) {
-      size_t bytes = n * (size_t)(2 * L) * 4;
-      void* p = cx.ensure(B_POINTS, bytes);
-      CK(cudaMemcpyAsync(p, points, bytes, cudaMemcpyHostToDevice, cx.s_copy));
-      CK(cudaEventRecord(cx.ev_points, cx.s_copy));
-      d_points = (const uint32_t*)p;
+    if (sloc == ZKB200_HOST) d_scalars = (const uint64_t*)cx.ensure(B_SCALARS, (size_t)nmsm * n * nl * 8);
+    if (ploc == ZKB200_HOST) d_points = (const uint32_t*)cx.ensure(B_POINTS, n * (size_t)(2 * L) * 4);
+    for (int k = 0; k < K; k++) {
+      if (sloc == ZKB200_HOST) {
+        size_t off = (K == 1 ? 0 : lo[k]) * nl, cnt64 = (K == 1 ? (size_t)nmsm * n : lo[k + 1] - lo[k]) * nl;
+        CK(cudaMemcpyAsync((uint64_t*)d_scalars + off, scalars + off, cnt64 * 8, cudaMemcpyHostToDevice, cx.s_copy));
+        CK(cudaEventRecord(cx.ev_sc[k], cx.s_copy));
+      }
+      if (ploc == ZKB200_HOST) {
+        size_t off = lo[k] * (size_t)(2 * L), cnt32 = (lo[k + 1] - lo[k]) * (size_t)(2 * L);
+        CK(cudaMemcpyAsync((uint32_t*)d_points + off, (const uint32_t*)points + off, cnt32 * 4, cudaMemcpyHostToDevice, cx.s_copy));
+        CK(cudaEventRecord(cx.ev_pt[k], cx.s_copy));
+      }
     }
 
-    // ---- sort pairs by key inside every segment ----
-    const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
-    uint32_t* cnt = (uint32_t*)cx.ensure(B_CNT, (size_t)nseg * SORT_RADIX * tiles * 4);
+    // ---- work arrays (sized for the longest slice) ----
+    const size_t pairs_max = (size_t)nseg * nmax;
+    uint32_t* keys[2] = {(uint32_t*)cx.ensure(B_KEYS0, pairs_max * 4), (uint32_t*)cx.ensure(B_KEYS1, pairs_max * 4)};
+    uint32_t* vals[2] = {(uint32_t*)cx.ensure(B_VALS0, pairs_max * 4), (uint32_t*)cx.ensure(B_VALS1, pairs_max * 4)};
+    const int tiles_max = (int)((nmax + SORT_TILE - 1) / SORT_TILE);
+    uint32_t* cnt = (uint32_t*)cx.ensure(B_CNT, (size_t)nseg * SORT_RADIX * tiles_max * 4);
     uint32_t* rowsum = (uint32_t*)cx.ensure(B_ROWSUM, (size_t)nseg * SORT_RADIX * 4);
-    int cur = 0;
-    for (int shift = 0; shift < c; shift += 8) {
-      g_launches += 3;
-      sort_pass(s, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, nseg, shift, cnt, rowsum, tiles);
-      CK(cudaGetLastError());
-      cur ^= 1;
-    }
-    CK(cudaEventRecord(cx.ev[3], s));
-
-    // ---- bucket accumulation, reduction and window combination, pipelined over window groups ----
-    // The windows can be processed top-down in G groups ($ZKB200_GROUPS, default 1).  Main stream:
-    // accumulate + head fix-up of group g; side stream (higher priority): bucket reduction of group g and
-    // its share of the Horner chain, meant to run underneath the accumulation of group g-1.  Measured on
-    // B200 (profiles/r1_notes.md) this loses: every small side-stream launch waits for a resident
-    // accumulate CTA to retire, so G = 1 (everything in order on one stream) is the default.
-    Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)nseg * NB * sizeof(Mem));
-    CK(cudaMemsetAsync(buckets, 0, (size_t)nseg * NB * sizeof(Mem), s));  // ZZ = 0: every bucket starts at infinity
-    int G = 1;
-    if (nmsm == 1) {
-      const char* e = getenv("ZKB200_GROUPS");
-      G = e ? atoi(e) : 1;  // measured on B200: >1 loses (side-stream kernels starve behind resident accumulate CTAs)
-      if (G > W) G = W;
-      if (G > MAX_GROUPS) G = MAX_GROUPS;
-      if (G < 1) G = 1;
-    }
-    st.groups = G;
-    const int Wg_max = (W + G - 1) / G;                       // windows per group (the top group may hold fewer)
-    const int segs_max = nmsm == 1 ? Wg_max : nseg;           // segments handled by one group launch
+    const size_t slice_stride = (size_t)nseg * NB;   // buckets per slice
+    Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)K * slice_stride * sizeof(Mem));
+    CK(cudaMemsetAsync(buckets, 0, (size_t)K * slice_stride * sizeof(Mem), s));  // ZZ = 0: every bucket starts at infinity
     static int resident_cache[2] = {0, 0};
     int& resident = resident_cache[C::Fp::L == 8 ? 0 : 1];
     if (resident == 0) resident = accumulate_resident_threads<C>();
-    // Sorted pairs per thread: the grid of every group is a whole number of waves of resident threads so
-    // that all SMs drain together (a partial last wave costs a full chunk time); about 48 insertions each.
+    // Sorted pairs per thread: every accumulate grid is a whole number of waves of resident threads so that
+    // all SMs drain together; about 48 insertions per thread for small problems (several waves), up to 192
+    // for big ones (fewer chunk heads to fold afterwards, still >= 12 waves).
     int chunk;
     {
       const char* e = getenv("ZKB200_CHUNK");
       if (e && atoi(e) > 0) {
         chunk = atoi(e);
       } else {
-        size_t gpairs = (size_t)segs_max * n;
-        // 48 insertions per thread keep small problems at several waves; big ones take longer chunks
-        // (up to 192) so that fewer chunk heads have to be folded afterwards, still >= 12 waves.
-        double target = (double)gpairs / ((double)resident * 12.0);
+        double target = (double)pairs_max / ((double)resident * 12.0);
         if (target < 48.0) target = 48.0;
         if (target > 192.0) target = 192.0;
-        double waves = (double)gpairs / ((double)resident * target);
+        double waves = (double)pairs_max / ((double)resident * target);
         size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
-        size_t per_seg_threads = ((size_t)resident * nw) / (size_t)segs_max;  // threads available to one segment
+        size_t per_seg_threads = ((size_t)resident * nw) / (size_t)nseg;  // threads available to one segment
         if (per_seg_threads < 1) per_seg_threads = 1;
-        size_t ch = (n + per_seg_threads - 1) / per_seg_threads;
+        size_t ch = (nmax + per_seg_threads - 1) / per_seg_threads;
         if (ch < 8) ch = 8;
         if (ch > 1024) ch = 1024;
         chunk = (int)ch;
       }
     }
-    const uint32_t chunks_per_seg = (uint32_t)((n + chunk - 1) / chunk);
-    const size_t nthreads_max = (size_t)segs_max * chunks_per_seg;
-    Mem* heads = (Mem*)cx.ensure(B_HEADS, nthreads_max * sizeof(Mem));
-    uint32_t* head_keys = (uint32_t*)cx.ensure(B_HEADKEYS, nthreads_max * 4);
-    const size_t cap2 = (size_t)segs_max * ((chunks_per_seg + FIXUP_FAN - 1) / FIXUP_FAN);
+    const uint32_t cps_max = (uint32_t)((nmax + chunk - 1) / chunk);
+    Mem* heads = (Mem*)cx.ensure(B_HEADS, (size_t)nseg * cps_max * sizeof(Mem));
+    uint32_t* head_keys = (uint32_t*)cx.ensure(B_HEADKEYS, (size_t)nseg * cps_max * 4);
+    const size_t cap2 = (size_t)nseg * ((cps_max + FIXUP_FAN - 1) / FIXUP_FAN);
     Mem* heads2 = (Mem*)cx.ensure(B_HEADS2, cap2 * sizeof(Mem));
     uint32_t* head_keys2 = (uint32_t*)cx.ensure(B_HEADKEYS2, cap2 * 4);
-    // reduction level plan (same for every group)
-    int log_m1 = 0;
-    if (c - 1 > 0) {
-      log_m1 = ilog2_floor(((size_t)segs_max << (c - 1)) / 65536 + 1);
-      if (log_m1 < 1) log_m1 = 1;
-      if (log_m1 > 5) log_m1 = 5;
-      if (log_m1 > c - 1) log_m1 = c - 1;
-    }
-    const size_t u0_cap = (size_t)segs_max << (c - 1 - log_m1);
-    Mem* Ub[2] = {(Mem*)cx.ensure(B_U0, u0_cap * sizeof(Mem)), (Mem*)cx.ensure(B_U1, (u0_cap / 2 + 1) * sizeof(Mem))};
-    Mem* Vb[2] = {(Mem*)cx.ensure(B_V0, u0_cap * sizeof(Mem)), (Mem*)cx.ensure(B_V1, (u0_cap / 2 + 1) * sizeof(Mem))};
-    Mem* state = (Mem*)cx.ensure(B_STATE, (size_t)nmsm * sizeof(Mem));
-    cudaStream_t side = cx.s_side;
 
-    if (ploc == ZKB200_HOST) CK(cudaStreamWaitEvent(s, cx.ev_points, 0));
-    CK(cudaEventRecord(cx.ev[4], s));
-    bool started = false;
-    for (int g = G - 1; g >= 0; g--) {
-      // segment range of this group (single MSM: windows [w0, w1); batch: everything)
-      int s0 = 0, s1 = nseg;
-      if (nmsm == 1) { s0 = g * Wg_max; s1 = s0 + Wg_max < W ? s0 + Wg_max : W; }
-      if (s1 <= s0) continue;
-      st.group_ran[g] = true;
-      const int gs = s1 - s0;
-      const uint32_t* gk = keys[cur] + (size_t)s0 * n;
-      const uint32_t* gv = vals[cur] + (size_t)s0 * n;
-      Mem* gb = buckets + (size_t)s0 * NB;
-      cudaEvent_t* ge = cx.gev + 6 * g;
-      CK(cudaEventRecord(ge[0], s));
+    for (int k = 0; k < K; k++) {
+      const size_t nk = lo[k + 1] - lo[k];
+      if (nk == 0) continue;
+      st.group_ran[k] = true;
+      cudaEvent_t* ge = cx.gev + 6 * k;
+      // ---- recode + sort this slice's pairs (segment-major with stride nk) ----
+      if (sloc == ZKB200_HOST) CK(cudaStreamWaitEvent(s, cx.ev_sc[k], 0));
+      CK(cudaEventRecord(ge[3], s));
       g_launches++;
-      launch_accumulate<C>(s, gk, gv, d_points, n, gs, chunk, chunks_per_seg, NB, gb, heads, head_keys);
+      launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, keys[0], vals[0]);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(ge[5], s));
+      const int tiles = (int)((nk + SORT_TILE - 1) / SORT_TILE);
+      int cur = 0;
+      for (int shift = 0; shift < c; shift += 8) {
+        g_launches += 3;
+        sort_pass(s, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nk, nseg, shift, cnt, rowsum, tiles);
+        CK(cudaGetLastError());
+        cur ^= 1;
+      }
+      CK(cudaEventRecord(ge[4], s));
+      // ---- bucket accumulation of this slice ----
+      if (ploc == ZKB200_HOST) CK(cudaStreamWaitEvent(s, cx.ev_pt[k], 0));
+      CK(cudaEventRecord(ge[0], s));
+      const uint32_t cps = (uint32_t)((nk + chunk - 1) / chunk);
+      g_launches++;
+      Mem* kb_ = buckets + (size_t)k * slice_stride;
+      launch_accumulate<C>(s, keys[cur], vals[cur], d_points + lo[k] * (size_t)(2 * L), nk, nseg, chunk, cps, NB, kb_, heads,
+                           head_keys);
       CK(cudaGetLastError());
       CK(cudaEventRecord(ge[1], s));
-      {  // fold the chunk heads into the buckets: log_FAN(chunks_per_seg) small levels
-        uint32_t T = chunks_per_seg;
+      {  // fold the chunk heads into the buckets: log_FAN(chunks) small levels
+        uint32_t T = cps;
         Mem* hb[2] = {heads, heads2};
         uint32_t* kb[2] = {head_keys, head_keys2};
         int src = 0;
@@ -331,7 +316,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
           uint32_t T_out = (T + FIXUP_FAN - 1) / FIXUP_FAN;
           int last = T_out == 1;
           g_launches++;
-          launch_fixup_level<C>(s, kb[src], hb[src], T, kb[src ^ 1], hb[src ^ 1], T_out, gs, NB, gb, last);
+          launch_fixup_level<C>(s, kb[src], hb[src], T, kb[src ^ 1], hb[src ^ 1], T_out, nseg, NB, kb_, last);
           CK(cudaGetLastError());
           if (last) break;
           T = T_out;
@@ -339,55 +324,63 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         }
       }
       CK(cudaEventRecord(ge[2], s));
-      // ---- side stream: reduce this group's buckets, then continue the Horner chain ----
-      cudaStream_t r = G > 1 ? side : s;
-      if (G > 1) CK(cudaStreamWaitEvent(r, ge[2], 0));
-      CK(cudaEventRecord(ge[3], r));
-      int logS = c - 1;
-      size_t total_out = (size_t)gs << (logS - log_m1);
-      g_launches++;
-      launch_reduce_first<C>(r, gb, total_out, log_m1, Ub[0], Vb[0]);
-      CK(cudaGetLastError());
-      logS -= log_m1;
-      int log_M = log_m1, lv = 0;
-      while (logS > 0) {
-        int lm = logS > 3 ? 3 : logS;
-        total_out = (size_t)gs << (logS - lm);
-        g_launches++;
-        launch_reduce_next<C>(r, Ub[lv], Vb[lv], total_out, lm, log_M, Ub[lv ^ 1], Vb[lv ^ 1]);
-        CK(cudaGetLastError());
-        logS -= lm;
-        log_M += lm;
-        lv ^= 1;
-      }
-      CK(cudaEventRecord(ge[4], r));
-      g_launches++;
-      launch_tail<C>(r, Ub[lv], nmsm, nmsm == 1 ? gs : W, c, out_mode, d_out, state, !started, g == 0);
-      started = true;
-      CK(cudaGetLastError());
-      CK(cudaEventRecord(ge[5], r));
     }
-    fin = G > 1 ? side : s;
+
+    // ---- bucket reduction by levels ----
+    CK(cudaEventRecord(cx.ev[5], s));
+    int log_m1 = 0;
+    if (c - 1 > 0) {
+      log_m1 = ilog2_floor(((size_t)nseg << (c - 1)) / 65536 + 1);
+      if (log_m1 < 1) log_m1 = 1;
+      if (log_m1 > 5) log_m1 = 5;
+      if (log_m1 > c - 1) log_m1 = c - 1;
+    }
+    int logS = c - 1;
+    size_t total_out = (size_t)nseg << (logS - log_m1);
+    Mem* Ub[2] = {(Mem*)cx.ensure(B_U0, total_out * sizeof(Mem)), (Mem*)cx.ensure(B_U1, (total_out / 2 + 1) * sizeof(Mem))};
+    Mem* Vb[2] = {(Mem*)cx.ensure(B_V0, total_out * sizeof(Mem)), (Mem*)cx.ensure(B_V1, (total_out / 2 + 1) * sizeof(Mem))};
+    g_launches++;
+    launch_reduce_first<C>(s, buckets, K, slice_stride, total_out, log_m1, Ub[0], Vb[0]);
+    CK(cudaGetLastError());
+    logS -= log_m1;
+    int log_M = log_m1, lv = 0;
+    while (logS > 0) {
+      int lm = logS > 3 ? 3 : logS;
+      total_out = (size_t)nseg << (logS - lm);
+      g_launches++;
+      launch_reduce_next<C>(s, Ub[lv], Vb[lv], total_out, lm, log_M, Ub[lv ^ 1], Vb[lv ^ 1]);
+      CK(cudaGetLastError());
+      logS -= lm;
+      log_M += lm;
+      lv ^= 1;
+    }
+    CK(cudaEventRecord(cx.ev[6], s));
+    // ---- window combination (Horner) + output conversion ----
+    g_launches++;
+    launch_tail<C>(s, Ub[lv], nmsm, W, c, out_mode, d_out, nullptr, 1, 1);
+    CK(cudaGetLastError());
     st.have_groups = true;
   }
-  CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, fin));
-  CK(cudaEventRecord(cx.ev[8], fin));
-  CK(cudaStreamSynchronize(fin));
+  CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(cx.ev[8], s));
   CK(cudaStreamSynchronize(s));
-  if (ploc == ZKB200_HOST && n) CK(cudaStreamSynchronize(cx.s_copy));
+  CK(cudaStreamSynchronize(cx.s_copy));
   for (int m = 0; m < nmsm; m++)
     memcpy((uint32_t*)out + (size_t)m * out_coords * L, h_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4);
-  for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&st.ms[i], cx.ev[i], cx.ev[i + 1]));
   if (st.have_groups) {
-    for (int g = 0; g < st.groups; g++) {
-      if (!st.group_ran[g]) continue;
-      float t;
-      cudaEvent_t* ge = cx.gev + 6 * g;
-      if (cudaEventElapsedTime(&t, ge[0], ge[1]) == cudaSuccess) st.ms[4] += t; else (void)cudaGetLastError();
-      if (cudaEventElapsedTime(&t, ge[1], ge[2]) == cudaSuccess) st.ms[5] += t; else (void)cudaGetLastError();
-      if (cudaEventElapsedTime(&t, ge[3], ge[4]) == cudaSuccess) st.ms[6] += t; else (void)cudaGetLastError();
-      if (cudaEventElapsedTime(&t, ge[4], ge[5]) == cudaSuccess) st.ms[7] += t; else (void)cudaGetLastError();
+    // phase times summed over the slices (CUDA events on the launching stream)
+    const int map[5][3] = {{3, 5, 1}, {5, 4, 2}, {4, 0, 3}, {0, 1, 4}, {1, 2, 5}};  // {from, to, stats slot}
+    for (int k = 0; k < st.groups; k++) {
+      if (!st.group_ran[k]) continue;
+      cudaEvent_t* ge = cx.gev + 6 * k;
+      for (auto& mp : map) {
+        float t;
+        CK(cudaEventElapsedTime(&t, ge[mp[0]], ge[mp[1]]));
+        st.ms[mp[2]] += t;
+      }
     }
+    CK(cudaEventElapsedTime(&st.ms[6], cx.ev[5], cx.ev[6]));
+    CK(cudaEventElapsedTime(&st.ms[7], cx.ev[6], cx.ev[8]));
   }
   CK(cudaEventElapsedTime(&st.ms[8], cx.ev[0], cx.ev[8]));
   cx.stats = st;
