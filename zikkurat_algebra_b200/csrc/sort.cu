@@ -78,7 +78,7 @@ k_sort_rowscan(uint32_t* __restrict__ cnt, uint32_t* __restrict__ rowsum, int ti
 
 // Scatter kernel with shared-memory staging on both sides:
 //   1. the tile's 4096 pairs are read with 128-bit loads into shared memory;
-//   2. every warp ranks its 512 items in index order (stable): __match_any_sync groups equal digits,
+//   2. every warp ranks its items in index order (stable): ballots group the lanes with equal digits,
 //      the group leader bumps the warp's digit counter;
 //   3. per-digit scan over the warps + scan over the digits give each item its slot in the tile's
 //      sorted order; the items are written to that slot in shared memory;
@@ -139,17 +139,33 @@ k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     key[i] = ok ? s_key[idx] : 0u;
     val[i] = ok ? s_val[idx] : 0u;
   }
+  // all peer masks first (independent of each other), then the serial counter updates
+  uint32_t peers[SORT_ITEMS];
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     uint32_t idx = wbase + i * 32 + lane;
     uint32_t d = (idx < count) ? ((key[i] >> shift) & 0xffu) : (uint32_t)SORT_RADIX;  // tail lanes share a dummy bin
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    int leader = __ffs(peers) - 1;
-    uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    // lanes with the same 9-bit value, from 9 ballots (MATCH.ANY costs one round per DISTINCT value in the
+    // warp, ~30 here; the ballot form is a fixed 9 votes + 9 logic ops)
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; b++) {
+      bool bit = (d >> b) & 1u;
+      uint32_t bal = __ballot_sync(0xffffffffu, bit);
+      m &= bit ? bal : ~bal;
+    }
+    peers[i] = m;
+  }
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) {
+    uint32_t idx = wbase + i * 32 + lane;
+    uint32_t d = (idx < count) ? ((key[i] >> shift) & 0xffu) : (uint32_t)SORT_RADIX;
+    int leader = __ffs(peers[i]) - 1;
+    uint32_t before = __popc(peers[i] & ((1u << lane) - 1u));
     uint32_t old = 0;
     if (lane == leader) {
       old = wcnt[warp][d];
-      wcnt[warp][d] = (uint16_t)(old + __popc(peers));
+      wcnt[warp][d] = (uint16_t)(old + __popc(peers[i]));
     }
     old = __shfl_sync(0xffffffffu, old, leader);
     off[i] = old + before;
