@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--logn", type=int, default=20, help="log2(points per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--pageable", action="store_true", help="also time the host-buffer path with ordinary (pageable) numpy arrays")
     return ap.parse_args()
 
 
@@ -261,6 +262,15 @@ def main():
         step_e2e()
     ms_e2e, res_e2e, _, _, _ = timed(step_e2e, args.steps)
 
+    ms_pageable = None
+    if args.pageable:
+        pg_pts, pg_sc = np.array(np_pts, copy=True), np.array(np_sc, copy=True)   # ordinary malloc'ed memory
+
+        def step_pageable():
+            return msm_sharded(curve, pg_sc, pg_pts, mont=True, resident=False, window=args.window)
+        for _ in range(2):
+            step_pageable()
+        ms_pageable, _, _, _, _ = timed(step_pageable, args.steps)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -309,6 +319,7 @@ def main():
                     "h2d_bytes_per_step": int(world * (np_sc.nbytes + np_pts.nbytes)),
                     "d2h_bytes_per_step": int(world * part_words * 8),
                     "host_memory": "pinned (torch pin_memory), passed as plain pointers to the reference-named C symbol path"},
+            "e2e_pageable_ms_per_step": (ms_pageable / args.steps) if ms_pageable else None,
             "gpu_launches": int(launches), "roofline": roofline,
             "phase_ms": stats["phase_ms"]}
     if not args.no_cpu_baseline and world == 1:

@@ -59,6 +59,12 @@ struct DeviceCtx {
   size_t cap[B_COUNT] = {0};
   uint32_t* h_out = nullptr;  // pinned staging for results
   size_t h_out_cap = 0;
+  // pinned staging ring for pageable host inputs (see host_to_device)
+  static constexpr int STAGE_SLOTS = 8;
+  static constexpr size_t STAGE_BYTES = (size_t)4 << 20;
+  uint8_t* stage = nullptr;
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr};
+  bool stage_used[STAGE_SLOTS] = {false};
   std::mutex mu;              // one MSM at a time per device (workspaces are shared)
   Stats stats;
 
@@ -132,6 +138,49 @@ DeviceCtx& get_ctx(int d = -1) {
     }
   }
   return cx;
+}
+
+// Host -> device copy that is fast for ORDINARY (pageable) memory too.  The reference's callers hand over
+// GHC-heap buffers (mallocForeignPtrBytes, lib/src/ZK/Algebra/Class/Flat.hs:186-194), which the driver copies
+// through its own bounce buffer at ~10 GB/s on one thread.  Here 4 host threads copy 4 MiB chunks into a
+// ring of pinned buffers and each chunk is sent with an async DMA as soon as it is staged, so the host-side
+// copy runs at several threads' memory bandwidth and overlaps with the PCIe transfer.  Pinned (registered)
+// source memory skips all that and is sent directly.  Returns when every chunk has been queued on `stream`.
+void host_to_device(DeviceCtx& cx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return;
+  cudaPointerAttributes attr;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+  else (void)cudaGetLastError();
+  if (pinned || bytes < ((size_t)2 << 20) || getenv("ZKB200_NO_STAGING")) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return;
+  }
+  constexpr int R = DeviceCtx::STAGE_SLOTS;
+  constexpr size_t CH = DeviceCtx::STAGE_BYTES;
+  if (!cx.stage) {
+    CK(cudaMallocHost((void**)&cx.stage, R * CH));
+    for (int i = 0; i < R; i++) CK(cudaEventCreateWithFlags(&cx.stage_ev[i], cudaEventDisableTiming));
+  }
+  const size_t nchunks = (bytes + CH - 1) / CH;
+  const int T = 4;                       // R is a multiple of T: a slot is always reused by the same thread
+  const int dev = cx.dev;
+  std::vector<std::thread> th;
+  for (int w = 0; w < T; w++) {
+    th.emplace_back([&, w] {
+      if (cudaSetDevice(dev) != cudaSuccess) abort();
+      for (size_t i = w; i < nchunks; i += T) {
+        const int slot = (int)(i % R);
+        if (cx.stage_used[slot]) CK(cudaEventSynchronize(cx.stage_ev[slot]));   // previous DMA out of this slot finished
+        const size_t off = i * CH, len = bytes - off < CH ? bytes - off : CH;
+        memcpy(cx.stage + (size_t)slot * CH, (const uint8_t*)src + off, len);
+        CK(cudaMemcpyAsync((uint8_t*)dst + off, cx.stage + (size_t)slot * CH, len, cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(cx.stage_ev[slot], stream));
+        cx.stage_used[slot] = true;
+      }
+    });
+  }
+  for (auto& t : th) t.join();
 }
 
 struct DeviceGuard {  // run on our device, then give the caller its own current device back
@@ -216,23 +265,11 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     lo[K] = n;
     for (int k = 0; k < K; k++) if (lo[k + 1] - lo[k] > nmax) nmax = lo[k + 1] - lo[k];
 
-    // ---- inputs -> device: all copies are queued now, in the order they are consumed ----
+    // ---- inputs -> device: copy stream, queued slice by slice just before the work that needs them ----
     const uint64_t* d_scalars = scalars;
     const uint32_t* d_points = (const uint32_t*)points;
     if (sloc == ZKB200_HOST) d_scalars = (const uint64_t*)cx.ensure(B_SCALARS, (size_t)nmsm * n * nl * 8);
     if (ploc == ZKB200_HOST) d_points = (const uint32_t*)cx.ensure(B_POINTS, n * (size_t)(2 * L) * 4);
-    for (int k = 0; k < K; k++) {
-      if (sloc == ZKB200_HOST) {
-        size_t off = (K == 1 ? 0 : lo[k]) * nl, cnt64 = (K == 1 ? (size_t)nmsm * n : lo[k + 1] - lo[k]) * nl;
-        CK(cudaMemcpyAsync((uint64_t*)d_scalars + off, scalars + off, cnt64 * 8, cudaMemcpyHostToDevice, cx.s_copy));
-        CK(cudaEventRecord(cx.ev_sc[k], cx.s_copy));
-      }
-      if (ploc == ZKB200_HOST) {
-        size_t off = lo[k] * (size_t)(2 * L), cnt32 = (lo[k + 1] - lo[k]) * (size_t)(2 * L);
-        CK(cudaMemcpyAsync((uint32_t*)d_points + off, (const uint32_t*)points + off, cnt32 * 4, cudaMemcpyHostToDevice, cx.s_copy));
-        CK(cudaEventRecord(cx.ev_pt[k], cx.s_copy));
-      }
-    }
 
     // ---- work arrays (sized for the longest slice) ----
     const size_t pairs_max = (size_t)nseg * nmax;
@@ -282,7 +319,12 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       st.group_ran[k] = true;
       cudaEvent_t* ge = cx.gev + 6 * k;
       // ---- recode + sort this slice's pairs (segment-major with stride nk) ----
-      if (sloc == ZKB200_HOST) CK(cudaStreamWaitEvent(s, cx.ev_sc[k], 0));
+      if (sloc == ZKB200_HOST) {
+        size_t off = (K == 1 ? 0 : lo[k]) * nl, cnt64 = (K == 1 ? (size_t)nmsm * n : nk) * nl;
+        host_to_device(cx, (uint64_t*)d_scalars + off, scalars + off, cnt64 * 8, cx.s_copy);
+        CK(cudaEventRecord(cx.ev_sc[k], cx.s_copy));
+        CK(cudaStreamWaitEvent(s, cx.ev_sc[k], 0));
+      }
       CK(cudaEventRecord(ge[3], s));
       g_launches++;
       launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, keys[0], vals[0]);
@@ -298,7 +340,12 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       }
       CK(cudaEventRecord(ge[4], s));
       // ---- bucket accumulation of this slice ----
-      if (ploc == ZKB200_HOST) CK(cudaStreamWaitEvent(s, cx.ev_pt[k], 0));
+      if (ploc == ZKB200_HOST) {
+        size_t off = lo[k] * (size_t)(2 * L), cnt32 = nk * (size_t)(2 * L);
+        host_to_device(cx, (uint32_t*)d_points + off, (const uint32_t*)points + off, cnt32 * 4, cx.s_copy);
+        CK(cudaEventRecord(cx.ev_pt[k], cx.s_copy));
+        CK(cudaStreamWaitEvent(s, cx.ev_pt[k], 0));
+      }
       CK(cudaEventRecord(ge[0], s));
       const uint32_t cps = (uint32_t)((nk + chunk - 1) / chunk);
       g_launches++;
