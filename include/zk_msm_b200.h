@@ -69,6 +69,16 @@ void bls12_381_G1_proj_batch_from_affine (int N, const uint64_t *src, uint64_t *
 void bls12_381_G1_jac_batch_to_affine    (int N, const uint64_t *src, uint64_t *tgt);
 void bls12_381_G1_jac_batch_from_affine  (int N, const uint64_t *src, uint64_t *tgt);
 
+/* ---- scope row 8f.2: Fr number-theoretic transform, same names and signatures as the reference
+ * (lib/cbits/curves/poly/mont/bn128_poly_mont.h:27-28, definitions bn128_poly_mont.c:418-525 and the bls12_381
+ * twin): src, tgt = 2^m canonical Montgomery Fr elements (natural order in and out), gen = generator of the
+ * order-2^m subgroup.  forward: tgt[k] = sum_j src[j] gen^(jk); inverse: tgt[j] = 2^-m sum_k src[k] gen^(-jk).
+ * Bit-identical output.  It is the step right before the MSM in a KZG commitment (examples/KZG.hs:96,139). */
+void bn128_poly_mont_ntt_forward    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bn128_poly_mont_ntt_inverse    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_poly_mont_ntt_forward(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_poly_mont_ntt_inverse(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+
 /* ---- extensions (not in the reference) -------------------------------------------------------- */
 enum { ZKB200_BN128 = 0, ZKB200_BLS12_381 = 1 };
 enum { ZKB200_OUT_PROJ = 0, ZKB200_OUT_JAC = 1, ZKB200_OUT_AFFINE = 2, ZKB200_OUT_XYZZ = 3 };

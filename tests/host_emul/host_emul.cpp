@@ -59,6 +59,9 @@ static Xyzz<P> sum_list(long n, const uint64_t* pts, const uint8_t* neg) {
   extern "C" void he_##NAME##_fp_neg(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_neg<C::Fp>(ld<C::Fp>(a))); } \
   extern "C" void he_##NAME##_fp_inv(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_inv<C::Fp>(ld<C::Fp>(a))); } \
   extern "C" void he_##NAME##_fp_inv_fermat(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_inv_fermat<C::Fp>(ld<C::Fp>(a))); } \
+  extern "C" void he_##NAME##_fr_sqr(const uint64_t* a, uint64_t* t) { st<C::Fr>(t, fe_sqr<C::Fr>(ld<C::Fr>(a))); }       \
+  extern "C" void he_##NAME##_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* t) {                       \
+    st<C::Fr>(t, fe_mul<C::Fr>(ld<C::Fr>(a), ld<C::Fr>(b))); }                                                  \
   extern "C" void he_##NAME##_fr_to_std(const uint64_t* a, uint64_t* t) {                                       \
     st<C::Fr>(t, fe_from_mont<C::Fr>(ld<C::Fr>(a))); }                                                          \
   extern "C" void he_##NAME##_sum_list(long n, const uint64_t* pts, const uint8_t* neg, uint64_t* t_aff) {      \

@@ -109,6 +109,23 @@ def test_fp_mul_matches_oracle_bytes(he, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_fr_mul_and_sqr(he, curve):
+    """Fr arithmetic as used by the NTT.  BLS12-381's r is ~0.45 * 2^256, so 3r does not fit 256 bits and
+    fe_sqr must take the general product there (the dedicated squaring's row bound needs 3*mod < 2^(32L))."""
+    cv = pyec.CURVES[curve]
+    rng = random.Random(8)
+    Rinv = pow(cv.Rr, -1, cv.r)
+    vals = [0, 1, cv.r - 1, cv.r - 2, (cv.r - 1) // 2] + [rng.randrange(cv.r) for _ in range(3000)]
+    vals += [cv.r - 1 - rng.randrange(1 << 64) for _ in range(500)]
+    for a in vals:
+        A = _arr(a.to_bytes(32, "little"))
+        assert int.from_bytes(refs.call2(he, f"he_{curve}_fr_sqr", A, 4).tobytes(), "little") == a * a * Rinv % cv.r
+        b = rng.randrange(cv.r)
+        B = _arr(b.to_bytes(32, "little"))
+        assert int.from_bytes(refs.call3(he, f"he_{curve}_fr_mul", A, B, 4).tobytes(), "little") == a * b * Rinv % cv.r
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_fr_to_std(he, curve):
     cv = pyec.CURVES[curve]
     rng = random.Random(3)

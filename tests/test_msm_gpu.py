@@ -364,3 +364,49 @@ def test_input_slices_give_identical_bytes(zk, curve):
             os.environ.pop("ZKB200_SLICES", None)
         else:
             os.environ["ZKB200_SLICES"] = old
+
+
+def _ntt_gen(cv, m):
+    """generator of the order-2^m subgroup of Fr^* (5 / 7 generate Fr^* for BN254 / BLS12-381)."""
+    g0 = 5 if cv.name == "bn128" else 7
+    s = ((cv.r - 1) & -(cv.r - 1)).bit_length() - 1
+    assert m <= s
+    g = pow(g0, (cv.r - 1) >> m, cv.r)
+    assert pow(g, 1 << m, cv.r) == 1 and (m == 0 or pow(g, 1 << (m - 1), cv.r) == cv.r - 1)
+    return g
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_fr_ntt_next_row(zk, curve):
+    """<curve>_poly_mont_ntt_forward / _inverse, bit-identical to the reference C
+    (lib/cbits/curves/poly/mont/bn128_poly_mont.c:418-525) and to a direct Python DFT at small sizes."""
+    cv = pyec.CURVES[curve]
+    rng = random.Random(5)
+    mont = lambda x: np.frombuffer(((x * cv.Rr) % cv.r).to_bytes(32, "little"), dtype=np.uint64)
+    unmont = lambda row: int.from_bytes(row.tobytes(), "little") * pow(cv.Rr, -1, cv.r) % cv.r
+    for m in (0, 1, 2, 3, 5, 8, 9, 10, 11, 14, 18):
+        N = 1 << m
+        g = _ntt_gen(cv, m)
+        xs = [rng.randrange(cv.r) for _ in range(N)] if m <= 11 else None
+        src = (np.stack([mont(x) for x in xs]) if xs is not None
+               else refs.random_scalars(curve, N, seed=m))               # any value < r is a valid Montgomery residue
+        gen = mont(g).copy()
+        fwd = zk.ntt(curve, m, gen, src)
+        if m <= 8:
+            want = [sum(xs[j] * pow(g, j * k, cv.r) for j in range(N)) % cv.r for k in range(N)]
+            assert [unmont(fwd[k]) for k in range(N)] == want
+        if refs.have_ref():
+            f = getattr(refs.ref(), f"{curve}_poly_mont_ntt_forward")
+            f.argtypes = [ctypes.c_int, refs.U64P, refs.U64P, refs.U64P]
+            f.restype = None
+            ref_out = np.zeros_like(src)
+            f(m, refs.ptr(gen), refs.ptr(np.ascontiguousarray(src).ravel()), refs.ptr(ref_out.ravel()))
+            assert fwd.tobytes() == ref_out.tobytes(), m
+            fi = getattr(refs.ref(), f"{curve}_poly_mont_ntt_inverse")
+            fi.argtypes = f.argtypes
+            fi.restype = None
+            ref_inv = np.zeros_like(src)
+            fi(m, refs.ptr(gen), refs.ptr(np.ascontiguousarray(src).ravel()), refs.ptr(ref_inv.ravel()))
+            assert zk.ntt(curve, m, gen, src, inverse=True).tobytes() == ref_inv.tobytes(), m
+        back = zk.ntt(curve, m, gen, fwd, inverse=True)
+        assert back.tobytes() == np.ascontiguousarray(src).tobytes(), m

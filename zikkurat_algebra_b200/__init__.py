@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 __all__ = [
-    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "call_reference_symbol",
+    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "NTT_SYMBOLS", "call_reference_symbol",
     "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
 ]
 
@@ -40,6 +40,7 @@ REFERENCE_SYMBOLS = [
     for o in (r, "affine")
 ] + [f"{c}_G1_{r}_MSM_std_coeff_{r}_out_variable" for c in ("bn128", "bls12_381") for r in ("proj", "jac")]
 CONVERT_SYMBOLS = [f"{c}_G1_{r}_batch_{d}_affine" for c in ("bn128", "bls12_381") for r in ("proj", "jac") for d in ("to", "from")]
+NTT_SYMBOLS = [f"{c}_poly_mont_ntt_{d}" for c in ("bn128", "bls12_381") for d in ("forward", "inverse")]
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
                      "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices"]
 
@@ -78,6 +79,10 @@ def lib() -> ctypes.CDLL:
         L.zkb200_launch_count.restype = ctypes.c_longlong
         L.zkb200_set_devices.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         L.zkb200_set_devices.restype = None
+        for name in NTT_SYMBOLS:
+            f = getattr(L, name)
+            f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P]
+            f.restype = None
         for name in CONVERT_SYMBOLS:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P]
@@ -166,6 +171,17 @@ def msm_device(curve: str, scalars_ptr: int, points_ptr: int, npoints: int, nmsm
     lib().zkb200_msm(cv["id"], nmsm, npoints, scalars_ptr, DEVICE, points_ptr, DEVICE, expo_nlimbs, int(mont), mode,
                      window, _ptr(res))
     return res
+
+
+def ntt(curve: str, m: int, gen: np.ndarray, src: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """Fr NTT of 2^m elements ((N, 4) uint64, canonical Montgomery form), the reference's
+    <curve>_poly_mont_ntt_forward / _inverse (natural order in and out)."""
+    a = _as_u64(src).reshape(-1, 4)
+    assert a.shape[0] == 1 << m
+    g = _as_u64(gen).ravel()
+    out = np.zeros_like(a)
+    getattr(lib(), f"{curve}_poly_mont_ntt_{'inverse' if inverse else 'forward'}")(m, _ptr(g), _ptr(a.ravel()), _ptr(out.ravel()))
+    return out
 
 
 def batch_to_affine(curve: str, pts: np.ndarray, repr: str = "proj") -> np.ndarray:

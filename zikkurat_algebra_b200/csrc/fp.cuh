@@ -120,6 +120,7 @@ ZK_HD void mont_mul_limbs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 // (0.57 for BN254, 0.31 for BLS12-381); final value (ab + cd + Mp)/R < p(1 + 2p/R) < 2p: one subtraction.
 template <class P>
 ZK_HD void mont_mul2_limbs(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d) {
+  static_assert(P::THREE_MOD_FITS, "fused product needs 3*mod < 2^(32L) (true for both Fp, false for BLS12-381 Fr)");
   constexpr int L = P::L;
   uint32_t A[L], B[L];
 #pragma unroll
@@ -186,6 +187,7 @@ ZK_HD Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
 // mont_mul2_limbs: each row adds a_i*W + m*p with W <= 2a < 2p, T stays below 2^(32(L+1)) because 3p < 2^(32L).
 template <class P>
 ZK_HD void mont_sqr_limbs(uint32_t* r, const uint32_t* a) {
+  static_assert(P::THREE_MOD_FITS, "dedicated squaring needs 3*mod < 2^(32L)");
   constexpr int L = P::L;
   uint32_t A[L], B[L], d[L];
   d[0] = a[0] << 1;  // unused as a multiplicand (row 0 uses a_0 itself), kept for uniform indexing
@@ -254,7 +256,8 @@ ZK_HD void mont_sqr_limbs(uint32_t* r, const uint32_t* a) {
 template <class P>
 ZK_HD Fe<P> fe_sqr(const Fe<P>& a) {
   Fe<P> r;
-  mont_sqr_limbs<P>(r.l, a.l);
+  if constexpr (P::THREE_MOD_FITS) mont_sqr_limbs<P>(r.l, a.l);
+  else mont_mul_limbs<P>(r.l, a.l, a.l);   // BLS12-381 Fr (r ~ 0.45 * 2^256): the row bound does not hold
   return r;
 }
 
@@ -270,9 +273,7 @@ __device__ __noinline__ Fe<P> fe_mul_call(Fe<P> a, Fe<P> b) {
 }
 template <class P>
 __device__ __noinline__ Fe<P> fe_sqr_call(Fe<P> a) {
-  Fe<P> r;
-  mont_sqr_limbs<P>(r.l, a.l);
-  return r;
+  return fe_sqr<P>(a);
 }
 template <class P>
 __device__ __noinline__ Fe<P> fe_mul2_call(Fe<P> a, Fe<P> b, Fe<P> c, Fe<P> d) {

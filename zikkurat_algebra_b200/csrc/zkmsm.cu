@@ -16,6 +16,7 @@
 
 #include "../../include/zk_msm_b200.h"
 #include "msm_common.cuh"
+#include "ntt.cuh"
 #include "sort.cuh"
 
 using namespace zk;
@@ -34,7 +35,7 @@ namespace {
 
 enum Buf {
   B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
-  B_U0, B_V0, B_U1, B_V1, B_STATE, B_OUT, B_COUNT
+  B_U0, B_V0, B_U1, B_V1, B_STATE, B_OUT, B_NTT_TABLE, B_COUNT
 };
 constexpr int N_EV = 9;
 constexpr int MAX_DEV = 16;
@@ -633,6 +634,29 @@ void run_convert(int N, const uint64_t* src, uint64_t* tgt, int jac, int to_affi
   CK(cudaStreamSynchronize(s));
 }
 
+// Fr NTT (scope row 8f.2): host buffers in, host buffers out
+template <class F>
+void run_ntt(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, int inverse) {
+  if (m < 0 || m > 30) { fprintf(stderr, "[zkmsm_b200] fatal: NTT size 2^%d unsupported\n", m); abort(); }
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  const size_t N = (size_t)1 << m, bytes = N * 32;
+  uint32_t* d_src = (uint32_t*)cx.ensure(B_SCALARS, bytes + 32);
+  uint32_t* d_tmp = (uint32_t*)cx.ensure(B_KEYS0, bytes);
+  uint32_t* d_dst = (uint32_t*)cx.ensure(B_KEYS1, bytes);
+  uint32_t* d_table = (uint32_t*)cx.ensure(B_NTT_TABLE, (N / 2 + 1) * 32);
+  uint32_t* d_gen = d_src + N * 8;
+  cudaStream_t s = cx.s_main;
+  CK(cudaMemcpyAsync(d_gen, gen, 32, cudaMemcpyHostToDevice, s));
+  host_to_device(cx, d_src, src, bytes, s);
+  g_launches += 1 + (m + 8) / 9;
+  ntt_device<F>(s, m, d_gen, d_src, d_tmp, d_dst, d_table, inverse);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+}
+
 }  // namespace
 
 // ---- exported C ABI -----------------------------------------------------------------------------------
@@ -743,6 +767,15 @@ const char* zkb200_version(void) { return "zkmsm_b200 0.1 (sm_100a)"; }
   void NAME##_G1_jac_batch_to_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE>(N, src, tgt, 1, 1); }    \
   void NAME##_G1_proj_batch_from_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE>(N, src, tgt, 0, 0); } \
   void NAME##_G1_jac_batch_from_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE>(N, src, tgt, 1, 0); }
+
+#define ZK_NTT_SYMBOLS(NAME, CURVE)                                                                                   \
+  void NAME##_poly_mont_ntt_forward(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                 \
+    run_ntt<CURVE::Fr>(m, gen, src, tgt, 0); }                                                                        \
+  void NAME##_poly_mont_ntt_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                 \
+    run_ntt<CURVE::Fr>(m, gen, src, tgt, 1); }
+
+ZK_NTT_SYMBOLS(bn128, Bn254)
+ZK_NTT_SYMBOLS(bls12_381, Bls12381)
 
 ZK_CONVERT_SYMBOLS(bn128, Bn254)
 ZK_CONVERT_SYMBOLS(bls12_381, Bls12381)
