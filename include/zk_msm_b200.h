@@ -103,6 +103,12 @@ void zkb200_sum_points(int curve, int k, const uint64_t *in, int in_mode, int ou
 void zkb200_gen_chain(int curve, unsigned long long start, long n, const uint64_t *p0_affine,
                       const uint64_t *d_affine, uint64_t *out, int out_loc);
 
+/* Fr NTT with explicit buffer locations (ZKB200_HOST / ZKB200_DEVICE): with device buffers the result can feed
+ * zkb200_msm's device-resident scalars directly -- a KZG commitment from evaluations (examples/KZG.hs:90-97:
+ * inverse NTT, then MSM over the SRS) without the coefficients ever leaving the GPU.  gen: host pointer. */
+void zkb200_ntt(int curve, int m, const uint64_t *gen, const uint64_t *src, int src_loc, uint64_t *tgt, int tgt_loc,
+                int inverse);
+
 /* Number of kernels this library has launched since it was loaded (bench.py's "gpu_launches"). */
 long long zkb200_launch_count(void);
 

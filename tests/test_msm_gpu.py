@@ -410,3 +410,27 @@ def test_fr_ntt_next_row(zk, curve):
             assert zk.ntt(curve, m, gen, src, inverse=True).tobytes() == ref_inv.tobytes(), m
         back = zk.ntt(curve, m, gen, fwd, inverse=True)
         assert back.tobytes() == np.ascontiguousarray(src).tobytes(), m
+
+
+def test_kzg_commit_from_values_stays_on_device(zk):
+    """examples/KZG.hs:90-97 (commitInterpolate): coefficients = inverse NTT of the evaluations, commitment =
+    MSM of the coefficients over the SRS.  Device-resident chain (zkb200_ntt -> zkb200_msm with device pointers)
+    against the same two steps through host memory and against the CPU reference."""
+    import torch
+    curve, m = "bn128", 12
+    cv = pyec.CURVES[curve]
+    N = 1 << m
+    gen = np.frombuffer(((_ntt_gen(cv, m) * cv.Rr) % cv.r).to_bytes(32, "little"), dtype=np.uint64).copy()
+    values = refs.random_scalars(curve, N, seed=4242)
+    srs = refs.chain_points(curve, N)
+    coeffs_host = zk.ntt(curve, m, gen, values, inverse=True)
+    want = zk.msm(curve, coeffs_host, srs, mont=True, out="affine")
+    assert want.tobytes() == cpu_affine(curve, coeffs_host, srs, "mont").tobytes()
+    d_vals = torch.from_numpy(values.view(np.int64)).cuda()
+    d_coef = torch.empty_like(d_vals)
+    d_srs = torch.from_numpy(srs.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    zk.ntt_device(curve, m, gen, d_vals.data_ptr(), d_coef.data_ptr(), inverse=True)
+    assert d_coef.cpu().numpy().view(np.uint64).tobytes() == coeffs_host.tobytes()
+    got = zk.msm_device(curve, d_coef.data_ptr(), d_srs.data_ptr(), N, mont=True, out="affine")[0]
+    assert got.tobytes() == want.tobytes()

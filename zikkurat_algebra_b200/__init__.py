@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 __all__ = [
-    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "NTT_SYMBOLS", "call_reference_symbol",
+    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "call_reference_symbol",
     "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
 ]
 
@@ -42,7 +42,7 @@ REFERENCE_SYMBOLS = [
 CONVERT_SYMBOLS = [f"{c}_G1_{r}_batch_{d}_affine" for c in ("bn128", "bls12_381") for r in ("proj", "jac") for d in ("to", "from")]
 NTT_SYMBOLS = [f"{c}_poly_mont_ntt_{d}" for c in ("bn128", "bls12_381") for d in ("forward", "inverse")]
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
-                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices"]
+                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt"]
 
 _U64P = ctypes.POINTER(ctypes.c_uint64)
 _lib: Optional[ctypes.CDLL] = None
@@ -79,6 +79,9 @@ def lib() -> ctypes.CDLL:
         L.zkb200_launch_count.restype = ctypes.c_longlong
         L.zkb200_set_devices.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         L.zkb200_set_devices.restype = None
+        L.zkb200_ntt.argtypes = [ctypes.c_int, ctypes.c_int, _U64P, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                 ctypes.c_int]
+        L.zkb200_ntt.restype = None
         for name in NTT_SYMBOLS:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P]
@@ -182,6 +185,12 @@ def ntt(curve: str, m: int, gen: np.ndarray, src: np.ndarray, inverse: bool = Fa
     out = np.zeros_like(a)
     getattr(lib(), f"{curve}_poly_mont_ntt_{'inverse' if inverse else 'forward'}")(m, _ptr(g), _ptr(a.ravel()), _ptr(out.ravel()))
     return out
+
+
+def ntt_device(curve: str, m: int, gen: np.ndarray, src_ptr: int, dst_ptr: int, inverse: bool = False) -> None:
+    """Same transform on device-resident buffers (raw device pointers, 2^m x 32 bytes each)."""
+    g = _as_u64(gen).ravel()
+    lib().zkb200_ntt(CURVES[curve]["id"], m, _ptr(g), src_ptr, DEVICE, dst_ptr, DEVICE, int(inverse))
 
 
 def batch_to_affine(curve: str, pts: np.ndarray, repr: str = "proj") -> np.ndarray:

@@ -634,26 +634,33 @@ void run_convert(int N, const uint64_t* src, uint64_t* tgt, int jac, int to_affi
   CK(cudaStreamSynchronize(s));
 }
 
-// Fr NTT (scope row 8f.2): host buffers in, host buffers out
+// Fr NTT (scope row 8f.2).  src / tgt may be host or device memory (device: the transform can feed
+// zkb200_msm's device-resident scalar input without leaving the GPU); gen is always a host pointer.
 template <class F>
-void run_ntt(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, int inverse) {
+void run_ntt(int m, const uint64_t* gen, const uint64_t* src, int src_loc, uint64_t* tgt, int tgt_loc, int inverse) {
   if (m < 0 || m > 30) { fprintf(stderr, "[zkmsm_b200] fatal: NTT size 2^%d unsupported\n", m); abort(); }
   DeviceCtx& cx = get_ctx();
   DeviceGuard guard(cx.dev);
   std::lock_guard<std::mutex> lk(cx.mu);
   const size_t N = (size_t)1 << m, bytes = N * 32;
-  uint32_t* d_src = (uint32_t*)cx.ensure(B_SCALARS, bytes + 32);
+  uint32_t* d_gen = (uint32_t*)cx.ensure(B_OUT, 4096);
   uint32_t* d_tmp = (uint32_t*)cx.ensure(B_KEYS0, bytes);
-  uint32_t* d_dst = (uint32_t*)cx.ensure(B_KEYS1, bytes);
   uint32_t* d_table = (uint32_t*)cx.ensure(B_NTT_TABLE, (N / 2 + 1) * 32);
-  uint32_t* d_gen = d_src + N * 8;
+  const uint32_t* d_src = (const uint32_t*)src;
+  uint32_t* d_dst = (uint32_t*)tgt;
+  if (tgt_loc != ZKB200_DEVICE || (const void*)tgt == (const void*)src) d_dst = (uint32_t*)cx.ensure(B_KEYS1, bytes);
   cudaStream_t s = cx.s_main;
   CK(cudaMemcpyAsync(d_gen, gen, 32, cudaMemcpyHostToDevice, s));
-  host_to_device(cx, d_src, src, bytes, s);
+  if (src_loc != ZKB200_DEVICE) {
+    uint32_t* p = (uint32_t*)cx.ensure(B_SCALARS, bytes);
+    host_to_device(cx, p, src, bytes, s);
+    d_src = p;
+  }
   g_launches += 1 + (m + 8) / 9;
   ntt_device<F>(s, m, d_gen, d_src, d_tmp, d_dst, d_table, inverse);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
+  if (tgt_loc != ZKB200_DEVICE) CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
+  else if ((void*)d_dst != (void*)tgt) CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToDevice, s));
   CK(cudaStreamSynchronize(s));
 }
 
@@ -687,6 +694,12 @@ void zkb200_set_devices(const int* devices, int count) {
 }
 
 long long zkb200_launch_count(void) { return g_launches.load(); }
+
+void zkb200_ntt(int curve, int m, const uint64_t* gen, const uint64_t* src, int src_loc, uint64_t* tgt, int tgt_loc, int inverse) {
+  if (curve == ZKB200_BN128) run_ntt<Bn254Fr>(m, gen, src, src_loc, tgt, tgt_loc, inverse);
+  else if (curve == ZKB200_BLS12_381) run_ntt<Bls12381Fr>(m, gen, src, src_loc, tgt, tgt_loc, inverse);
+  else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+}
 
 void zkb200_gen_chain(int curve, unsigned long long start, long n, const uint64_t* p0_affine, const uint64_t* d_affine,
                       uint64_t* out, int out_loc) {
@@ -770,9 +783,9 @@ const char* zkb200_version(void) { return "zkmsm_b200 0.1 (sm_100a)"; }
 
 #define ZK_NTT_SYMBOLS(NAME, CURVE)                                                                                   \
   void NAME##_poly_mont_ntt_forward(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                 \
-    run_ntt<CURVE::Fr>(m, gen, src, tgt, 0); }                                                                        \
+    run_ntt<CURVE::Fr>(m, gen, src, ZKB200_HOST, tgt, ZKB200_HOST, 0); }                                                                        \
   void NAME##_poly_mont_ntt_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                 \
-    run_ntt<CURVE::Fr>(m, gen, src, tgt, 1); }
+    run_ntt<CURVE::Fr>(m, gen, src, ZKB200_HOST, tgt, ZKB200_HOST, 1); }
 
 ZK_NTT_SYMBOLS(bn128, Bn254)
 ZK_NTT_SYMBOLS(bls12_381, Bls12381)
