@@ -66,15 +66,48 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   const uint32_t* vp = vals + (size_t)seg * n;
   XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
 
+  // Software pipeline for the random point gather: while entry e is being added, the point of entry e+1 is
+  // already on its way into this thread's shared-memory slot (cp.async, no registers held), and the
+  // (key, index) pair of entry e+2 is being read.  Slot layout [buffer][16-byte word][thread]: conflict-free.
+  constexpr int PW = (2 * P::L) / 4;                 // 16-byte words per affine point
+  __shared__ uint4 stage[2][PW][128];
+  auto prefetch = [&](int buf, uint32_t v) {
+    const uint4* src = reinterpret_cast<const uint4*>(points + (size_t)(v & 0x7fffffffu) * (2 * P::L));
+#pragma unroll
+    for (int w = 0; w < PW; w++) {
+      unsigned dst = (unsigned)__cvta_generic_to_shared(&stage[buf][w][threadIdx.x]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + w) : "memory");
+    }
+  };
   Xyzz<P> acc = xyzz_inf<P>();
   uint32_t cur = 0;      // key of the open run (0 = none)
   bool head_open = true;  // the open run is the chunk's first one
   uint32_t head_key = 0;
-  for (size_t e = start; e < end; e++) {
-    uint32_t key = kp[e];
-    if (key == 0) continue;  // digit 0: no insertion (these sort to the front of the segment)
-    uint32_t v = vp[e];
-    Affine<P> pt = load_affine<P>(points, v & 0x7fffffffu);
+  // skip the zero-digit prefix of the segment (digit 0 = no insertion; those pairs sort to the front)
+  size_t e = start;
+  while (e < end && kp[e] == 0) e++;
+  uint32_t key = 0, v = 0, key1 = 0, v1 = 0;
+  if (e < end) { key = kp[e]; v = vp[e]; prefetch((int)(e & 1), v); }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (e + 1 < end) { key1 = kp[e + 1]; v1 = vp[e + 1]; }
+  for (; e < end; e++) {
+    uint32_t key2 = 0, v2 = 0;
+    if (e + 1 < end) prefetch((int)((e + 1) & 1), v1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (e + 2 < end) { key2 = kp[e + 2]; v2 = vp[e + 2]; }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // the copy for entry e (previous group) has landed
+    Affine<P> pt;
+    {
+      uint32_t w32[2 * P::L];
+      const int buf = (int)(e & 1);
+#pragma unroll
+      for (int w = 0; w < PW; w++) {
+        uint4 q = stage[buf][w][threadIdx.x];
+        w32[4 * w] = q.x; w32[4 * w + 1] = q.y; w32[4 * w + 2] = q.z; w32[4 * w + 3] = q.w;
+      }
+#pragma unroll
+      for (int k = 0; k < P::L; k++) { pt.x.l[k] = w32[k]; pt.y.l[k] = w32[P::L + k]; }
+    }
     bool inf = affine_is_inf<P>(pt);
     Fe<P> ny = fe_neg<P>(pt.y);
     if (v >> 31) pt.y = ny;
@@ -88,7 +121,9 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
     } else if (!inf) {
       xyzz_madd<P, CALLS>(acc, pt);
     }
+    key = key1; v = v1; key1 = key2; v1 = v2;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (cur != 0) {
     if (head_open) { store_xyzz<P>(heads + t, acc); head_key = cur; }
     else store_xyzz<P>(bseg + (cur - 1), acc);
