@@ -137,28 +137,22 @@ ZK_D void write_result(uint32_t* o, const Xyzz<P>& acc, int mode) {
     write_fe<P>(o, X); write_fe<P>(o + L, Y); write_fe<P>(o + 2 * L, Z);
   }
 }
-// one 4-lane team per MSM of the batch; Rw[msm*Wg + w] = sums of the Wg windows of this call (top-down
-// Horner: acc = 2^c * acc + R_w).  The chain may be split over several launches (window groups): `state`
-// carries the accumulator, `first` starts from infinity, `last` converts and writes the result
-// (record stride 4L words).
+// one 4-lane team per MSM of the batch; Rw[msm*W + w] = window sums; top-down Horner: acc = 2^c * acc + R_w
+// (c inlined team doublings per window); then output conversion (record stride 4L words).
 template <class C>
 __global__ void __launch_bounds__(32)
-k_tail(const XyzzMem<typename C::Fp>* __restrict__ Rw, int nmsm, int Wg, int c, int mode, uint32_t* __restrict__ out,
-       XyzzMem<typename C::Fp>* __restrict__ state, int first, int last) {
+k_tail(const XyzzMem<typename C::Fp>* __restrict__ Rw, int nmsm, int W, int c, int mode, uint32_t* __restrict__ out) {
   using P = typename C::Fp;
   int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   if (m >= nmsm) return;
   Team tm;
-  Xyzz<P> acc = first ? xyzz_inf<P>() : load_xyzz<P>(state + m);
-  for (int w = Wg - 1; w >= 0; w--) {
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int w = W - 1; w >= 0; w--) {
 #pragma unroll 1
     for (int d = 0; d < c; d++) acc = xyzz_dbl_team<P>(tm, acc);   // inlined once; no-op while acc is infinity
-    xyzz_add_tm<P>(tm, acc, load_xyzz<P>(Rw + (size_t)m * Wg + w));
+    xyzz_add_tm<P>(tm, acc, load_xyzz<P>(Rw + (size_t)m * W + w));
   }
-  if (tm.t == 0) {
-    if (last) write_result<P>(out + (size_t)m * (4 * P::L), acc, mode);
-    else store_xyzz<P>(state + m, acc);
-  }
+  if (tm.t == 0) write_result<P>(out + (size_t)m * (4 * P::L), acc, mode);
 }
 
 // sum of k group elements given in one of the reference's representations (multi-GPU combine, K8)
@@ -301,9 +295,8 @@ void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, cons
   k_reduce_next<C><<<(unsigned)((total_out * 16 + 127) / 128), 128, 0, s>>>(Uin, Vin, total_out, log_m, log_M, Uout, Vout);
 }
 template <class C>
-void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int Wg, int c, int mode, uint32_t* out,
-                 XyzzMem<typename C::Fp>* state, int first, int last) {
-  k_tail<C><<<(nmsm * 4 + 31) / 32, 32, 0, s>>>(Rw, nmsm, Wg, c, mode, out, state, first, last);
+void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out) {
+  k_tail<C><<<(nmsm * 4 + 31) / 32, 32, 0, s>>>(Rw, nmsm, W, c, mode, out);
 }
 template <class C>
 void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out) {
@@ -315,8 +308,7 @@ void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, i
                                        XyzzMem<C::Fp>*);                                                                  \
   template void launch_reduce_next<C>(cudaStream_t, const XyzzMem<C::Fp>*, const XyzzMem<C::Fp>*, size_t, int, int,        \
                                       XyzzMem<C::Fp>*, XyzzMem<C::Fp>*);                                                   \
-  template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*, XyzzMem<C::Fp>*, int,   \
-                               int);                                                                                     \
+  template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*);                        \
   template void launch_sum_points<C>(cudaStream_t, const uint32_t*, int, int, int, uint32_t*);                             \
   template void launch_gen_chain<C>(cudaStream_t, const uint32_t*, unsigned long long, size_t, uint32_t*);               \
   template void launch_batch_to_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);                         \

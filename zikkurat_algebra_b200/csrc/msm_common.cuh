@@ -89,8 +89,7 @@ template <class C> void launch_reduce_first(cudaStream_t s, const XyzzMem<typena
 template <class C> void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin,
                                            size_t total_out, int log_m, int log_M, XyzzMem<typename C::Fp>* Uout,
                                            XyzzMem<typename C::Fp>* Vout);
-template <class C> void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int Wg, int c, int mode, uint32_t* out,
-                                    XyzzMem<typename C::Fp>* state, int first, int last);
+template <class C> void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out);
 template <class C> void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out);
 template <class C> void launch_batch_to_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);
 template <class C> void launch_batch_from_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);

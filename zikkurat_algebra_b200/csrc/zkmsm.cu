@@ -35,24 +35,24 @@ namespace {
 
 enum Buf {
   B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
-  B_U0, B_V0, B_U1, B_V1, B_STATE, B_OUT, B_NTT_TABLE, B_COUNT
+  B_U0, B_V0, B_U1, B_V1, B_OUT, B_NTT_TABLE, B_COUNT
 };
 constexpr int N_EV = 9;
 constexpr int MAX_DEV = 16;
 
 struct Stats {
   float ms[9] = {0};
-  int c = 0, W = 0, groups = 1;
-  bool have_groups = false;
-  bool group_ran[8] = {false};
+  int c = 0, W = 0, slices = 1;
+  bool have_phases = false;
+  bool slice_ran[8] = {false};
   long long insertions = 0;
 };
 constexpr int MAX_SLICES = 8;
 
 struct DeviceCtx {
-  bool ready = false;
+  std::atomic<bool> ready{false};
   int dev = 0;
-  cudaStream_t s_main = nullptr, s_copy = nullptr, s_side = nullptr;
+  cudaStream_t s_main = nullptr, s_copy = nullptr;
   cudaEvent_t ev[N_EV + 1] = {nullptr};
   cudaEvent_t gev[6 * 8] = {nullptr};  // per input slice: accumulate start/end, fix-up end, recode start, sort end, recode end
   cudaEvent_t ev_sc[8] = {nullptr}, ev_pt[8] = {nullptr};   // per input slice: scalars / points have arrived
@@ -123,11 +123,6 @@ DeviceCtx& get_ctx(int d = -1) {
       cx.dev = d;
       CK(cudaStreamCreateWithFlags(&cx.s_main, cudaStreamNonBlocking));
       CK(cudaStreamCreateWithFlags(&cx.s_copy, cudaStreamNonBlocking));
-      {
-        int least = 0, greatest = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        CK(cudaStreamCreateWithPriority(&cx.s_side, cudaStreamNonBlocking, greatest));
-      }
       for (int i = 0; i < 6 * 8; i++) CK(cudaEventCreate(&cx.gev[i]));
       for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
       for (int i = 0; i < 8; i++) {
@@ -234,7 +229,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   CK(cudaEventRecord(cx.ev[0], s));
   if (n == 0) {
     g_launches++;
-    launch_tail<C>(s, nullptr, nmsm, 0, 0, out_mode, d_out, nullptr, 1, 1);
+    launch_tail<C>(s, nullptr, nmsm, 0, 0, out_mode, d_out);
     CK(cudaGetLastError());
   } else {
     c = window > 0 ? window : pick_window(n, nmsm, nbits);
@@ -259,7 +254,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (K < 1) K = 1;
       if ((size_t)K > n) K = 1;
     }
-    st.groups = K;
+    st.slices = K;
     size_t lo[MAX_SLICES + 1];
     size_t nmax = 0;
     for (int k = 0; k <= K; k++) lo[k] = (n * (size_t)k / K) & ~(size_t)3;   // multiples of 4 keep 16-byte alignment
@@ -317,7 +312,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     for (int k = 0; k < K; k++) {
       const size_t nk = lo[k + 1] - lo[k];
       if (nk == 0) continue;
-      st.group_ran[k] = true;
+      st.slice_ran[k] = true;
       cudaEvent_t* ge = cx.gev + 6 * k;
       // ---- recode + sort this slice's pairs (segment-major with stride nk) ----
       if (sloc == ZKB200_HOST) {
@@ -405,9 +400,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     CK(cudaEventRecord(cx.ev[6], s));
     // ---- window combination (Horner) + output conversion ----
     g_launches++;
-    launch_tail<C>(s, Ub[lv], nmsm, W, c, out_mode, d_out, nullptr, 1, 1);
+    launch_tail<C>(s, Ub[lv], nmsm, W, c, out_mode, d_out);
     CK(cudaGetLastError());
-    st.have_groups = true;
+    st.have_phases = true;
   }
   CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(cx.ev[8], s));
@@ -415,11 +410,11 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   CK(cudaStreamSynchronize(cx.s_copy));
   for (int m = 0; m < nmsm; m++)
     memcpy((uint32_t*)out + (size_t)m * out_coords * L, h_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4);
-  if (st.have_groups) {
+  if (st.have_phases) {
     // phase times summed over the slices (CUDA events on the launching stream)
     const int map[5][3] = {{3, 5, 1}, {5, 4, 2}, {4, 0, 3}, {0, 1, 4}, {1, 2, 5}};  // {from, to, stats slot}
-    for (int k = 0; k < st.groups; k++) {
-      if (!st.group_ran[k]) continue;
+    for (int k = 0; k < st.slices; k++) {
+      if (!st.slice_ran[k]) continue;
       cudaEvent_t* ge = cx.gev + 6 * k;
       for (auto& mp : map) {
         float t;
