@@ -79,8 +79,21 @@ void bn128_poly_mont_ntt_inverse    (int m, const uint64_t *gen, const uint64_t 
 void bls12_381_poly_mont_ntt_forward(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
 void bls12_381_poly_mont_ntt_inverse(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
 
+/* ---- scope row 8f.3: G2 multi-scalar multiplication (points over Fp2 = Fp[u]/(u^2+1), coordinates c0 || c1),
+ * same names and signatures as the reference (lib/cbits/curves/g2/proj/bn128_G2_proj.h:43-46, definitions
+ * bn128_G2_proj.c:498-660 and the bls12_381 twin).  Same pipeline as G1 with Fp2 arithmetic; affine output is
+ * bit-identical, infinity = all 0xFF (2 x 2 coordinates), proj infinity = (0, 1, 0). */
+void bn128_G2_proj_MSM_std_coeff_proj_out      (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G2_proj_MSM_mont_coeff_proj_out     (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G2_proj_MSM_std_coeff_affine_out    (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G2_proj_MSM_mont_coeff_affine_out   (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G2_proj_MSM_std_coeff_proj_out  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G2_proj_MSM_mont_coeff_proj_out (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G2_proj_MSM_std_coeff_affine_out(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G2_proj_MSM_mont_coeff_affine_out(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+
 /* ---- extensions (not in the reference) -------------------------------------------------------- */
-enum { ZKB200_BN128 = 0, ZKB200_BLS12_381 = 1 };
+enum { ZKB200_BN128 = 0, ZKB200_BLS12_381 = 1, ZKB200_BN128_G2 = 2, ZKB200_BLS12_381_G2 = 3 };
 enum { ZKB200_OUT_PROJ = 0, ZKB200_OUT_JAC = 1, ZKB200_OUT_AFFINE = 2, ZKB200_OUT_XYZZ = 3 };
 enum { ZKB200_HOST = 0, ZKB200_DEVICE = 1 };
 

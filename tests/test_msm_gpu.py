@@ -434,3 +434,82 @@ def test_kzg_commit_from_values_stays_on_device(zk):
     assert d_coef.cpu().numpy().view(np.uint64).tobytes() == coeffs_host.tobytes()
     got = zk.msm_device(curve, d_coef.data_ptr(), d_srs.data_ptr(), N, mont=True, out="affine")[0]
     assert got.tobytes() == want.tobytes()
+
+
+def _g2_ref_chain(curve, n, step=3):
+    """n G2 points G, G+D, G+2D, ... (D = step*G) in affine Montgomery bytes, built with the reference's own
+    affine addition (CPU); (n, 4*nlimbs) uint64."""
+    lib = refs.ref()
+    W = 4 * refs.CURVE_LIMBS[curve]           # u64 words per affine G2 point (2 coordinates x 2 x nlimbs)
+    gen = (ctypes.c_uint64 * W).in_dll(lib, f"{curve}_G2_affine_gen_G2")
+    G = np.frombuffer(bytes(gen), dtype=np.uint64).copy()
+    D = G.copy()
+    for _ in range(step - 1):
+        D = refs.call3(lib, f"{curve}_G2_affine_add", D, G, W)
+    out = np.zeros((n, W), np.uint64)
+    P = G.copy()
+    for i in range(n):
+        out[i] = P
+        P = refs.call3(lib, f"{curve}_G2_affine_add", P, D, W)
+    return out
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_g2_msm_next_row(zk, curve):
+    """<curve>_G2_proj_MSM_{std,mont}_coeff_{proj,affine}_out against the reference C
+    (lib/cbits/curves/g2/proj/bn128_G2_proj.c:498-660): affine bytes identical, proj output equal after the
+    reference's G2_proj_to_affine; edge cases as for G1."""
+    if not refs.have_ref():
+        pytest.skip("needs oracle/_ref")
+    lib = refs.ref()
+    nl = refs.CURVE_LIMBS[curve]
+    W = 4 * nl
+    g2 = curve + "_g2"
+    pts_all = _g2_ref_chain(curve, 700)
+    for n in (0, 1, 2, 3, 33, 700):
+        pts = pts_all[:n]
+        for form in ("std", "mont"):
+            sc = refs.random_scalars(curve, n, seed=n + 5, reduce=(form == "mont"))
+            got = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_{form}_coeff_affine_out", sc, pts, npoints=n)
+            if n == 0:
+                assert got.tobytes() == b"\xff" * (8 * W)
+                continue
+            want = refs.call_msm(lib, f"{curve}_G2_proj_MSM_{form}_coeff_affine_out", sc.ravel(), pts.ravel(), W, n=n)
+            assert got.tobytes() == want.tobytes(), (n, form)
+            proj = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_{form}_coeff_proj_out", sc, pts, npoints=n)
+            assert refs.call2(lib, f"{curve}_G2_proj_to_affine", proj, W).tobytes() == want.tobytes(), (n, form)
+    # exceptional cases: P and -P, repeated points, infinity inputs, zero scalars
+    P, Q = pts_all[5].copy(), pts_all[9].copy()
+    negP = P.copy()
+    cvp = pyec.CURVES[curve].p
+    for off in (2 * nl, 3 * nl):               # y = (c0, c1): negate both components
+        y = int.from_bytes(P[off:off + nl].tobytes(), "little")
+        negP[off:off + nl] = np.frombuffer(((cvp - y) % cvp).to_bytes(8 * nl, "little"), dtype=np.uint64)
+    inf = np.full(W, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    cases = {
+        "p_minus_p": ([5, 5], [P, negP]),
+        "p_minus_p_more": ([5, 5, 9], [P, negP, Q]),
+        "repeated": ([3, 3, 3, 3], [P, P, P, P]),
+        "inf_inputs": ([9, 2, 1], [inf, P, inf]),
+        "zeros": ([0, 0], [P, Q]),
+        "full256": ([(1 << 256) - 1, 12345], [P, Q]),
+    }
+    cv = pyec.CURVES[curve]
+    for name, (ks, ps) in cases.items():
+        S = np.frombuffer(b"".join(cv.scalar_std_bytes(k) for k in ks), dtype=np.uint64).copy()
+        Pb = np.ascontiguousarray(np.stack(ps))
+        want = refs.call_msm(lib, f"{curve}_G2_proj_MSM_std_coeff_affine_out", S, Pb.ravel(), W)
+        got = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_std_coeff_affine_out", S, Pb)
+        assert got.tobytes() == want.tobytes(), name
+    # GPU chain generator for G2 == reference chain; larger size by the split property
+    D = refs.call3(lib, f"{curve}_G2_affine_add", refs.call3(lib, f"{curve}_G2_affine_add", pts_all[0].copy(), pts_all[0].copy(), W), pts_all[0].copy(), W)
+    assert zk.gen_chain(g2, 50, pts_all[0], D).tobytes() == pts_all[:50].tobytes()
+    n = 1 << 14
+    big = zk.gen_chain(g2, n, pts_all[0], D)
+    sc = refs.random_scalars(curve, n, seed=99)
+    whole = zk.msm(g2, sc, big, mont=True, out="affine")
+    parts = [zk.msm(g2, sc[i * (n // 4):(i + 1) * (n // 4)], big[i * (n // 4):(i + 1) * (n // 4)], mont=True, out="proj") for i in range(4)]
+    assert zk.sum_points(g2, np.stack(parts), "proj", "affine").tobytes() == whole.tobytes()
+    m = 1 << 11
+    want = refs.call_msm(lib, f"{curve}_G2_proj_MSM_mont_coeff_affine_out", sc[:m].ravel(), big[:m].ravel(), W, n=m)
+    assert zk.msm(g2, sc[:m], big[:m], mont=True, out="affine").tobytes() == want.tobytes()

@@ -19,14 +19,16 @@ from typing import Optional
 import numpy as np
 
 __all__ = [
-    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "call_reference_symbol",
+    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "G2_SYMBOLS", "call_reference_symbol",
     "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "lib", "libzkmsm_b200.so")
 
-CURVES = {"bn128": dict(id=0, nlimbs_p=4), "bls12_381": dict(id=1, nlimbs_p=6)}
+# nlimbs_p = uint64 words per point COORDINATE (G2 coordinates are Fp2 elements: c0 || c1)
+CURVES = {"bn128": dict(id=0, nlimbs_p=4), "bls12_381": dict(id=1, nlimbs_p=6),
+          "bn128_g2": dict(id=2, nlimbs_p=8), "bls12_381_g2": dict(id=3, nlimbs_p=12)}
 OUT_PROJ, OUT_JAC, OUT_AFFINE, OUT_XYZZ = 0, 1, 2, 3
 _OUT = {"proj": OUT_PROJ, "jac": OUT_JAC, "affine": OUT_AFFINE, "xyzz": OUT_XYZZ}
 _OUT_COORDS = {OUT_PROJ: 3, OUT_JAC: 3, OUT_AFFINE: 2, OUT_XYZZ: 4}
@@ -41,6 +43,7 @@ REFERENCE_SYMBOLS = [
 ] + [f"{c}_G1_{r}_MSM_std_coeff_{r}_out_variable" for c in ("bn128", "bls12_381") for r in ("proj", "jac")]
 CONVERT_SYMBOLS = [f"{c}_G1_{r}_batch_{d}_affine" for c in ("bn128", "bls12_381") for r in ("proj", "jac") for d in ("to", "from")]
 NTT_SYMBOLS = [f"{c}_poly_mont_ntt_{d}" for c in ("bn128", "bls12_381") for d in ("forward", "inverse")]
+G2_SYMBOLS = [f"{c}_G2_proj_MSM_{f}_coeff_{o}_out" for c in ("bn128", "bls12_381") for f in ("std", "mont") for o in ("proj", "affine")]
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
                      "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt"]
 
@@ -90,7 +93,7 @@ def lib() -> ctypes.CDLL:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P]
             f.restype = None
-        for name in REFERENCE_SYMBOLS:
+        for name in REFERENCE_SYMBOLS + G2_SYMBOLS:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P, ctypes.c_int] + ([ctypes.c_int] if name.endswith("_variable") else [])
             f.restype = None
@@ -122,7 +125,7 @@ def call_reference_symbol(name: str, scalars: np.ndarray, points: np.ndarray, np
     """Call one of the reference-named entry points exactly as the reference's FFI would
     (void f(int npoints, const uint64_t* expos, const uint64_t* grps, uint64_t* tgt, int expo_nlimbs))."""
     curve = "bls12_381" if name.startswith("bls12_381") else "bn128"
-    L = CURVES[curve]["nlimbs_p"]
+    L = CURVES[curve + ("_g2" if "_G2_" in name else "")]["nlimbs_p"]
     coords = 2 if "affine_out" in name else 3
     s = _as_u64(scalars).ravel()
     p = _as_u64(points).ravel()

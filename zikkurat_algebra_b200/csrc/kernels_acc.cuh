@@ -49,7 +49,7 @@ k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int
 // writer); the chunk's first run may continue a run of the previous chunk and goes to heads[t]
 // instead, to be folded in by k_fixup.  Work per thread is exactly `chunk` insertions whatever the
 // scalar distribution, so there is no bucket-size imbalance.
-template <class C, bool CALLS, int MINB = (C::Fp::L == 8 ? 4 : 3)>
+template <class C, bool CALLS, int MINB = (C::Fp::L <= 8 ? 4 : (C::Fp::L <= 12 ? 3 : 2))>
 __global__ void __launch_bounds__(128, MINB)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const uint32_t* __restrict__ points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,

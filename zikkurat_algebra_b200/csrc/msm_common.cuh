@@ -14,7 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "curve_params.cuh"
+#include "curves.cuh"
 #include "ec.cuh"
 #include "recode.cuh"
 

@@ -277,8 +277,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     const size_t slice_stride = (size_t)nseg * NB;   // buckets per slice
     Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)K * slice_stride * sizeof(Mem));
     CK(cudaMemsetAsync(buckets, 0, (size_t)K * slice_stride * sizeof(Mem), s));  // ZZ = 0: every bucket starts at infinity
-    static int resident_cache[2] = {0, 0};
-    int& resident = resident_cache[C::Fp::L == 8 ? 0 : 1];
+    static int resident = 0;   // one per curve (template instantiation)
     if (resident == 0) resident = accumulate_resident_threads<C>();
     // Sorted pairs per thread: every accumulate grid is a whole number of waves of resident threads so that
     // all SMs drain together; about 48 insertions per thread for small problems (several waves), up to 192
@@ -514,18 +513,26 @@ void run_multi(const std::vector<int>& devs, int nmsm, size_t n, const uint64_t*
 void msm_entry(int curve, int nmsm, long n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc, int nl,
                int mont, int out_mode, int window, uint64_t* out) {
   if (n < 0) n = 0;
-  if (curve != ZKB200_BN128 && curve != ZKB200_BLS12_381) { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+  if (curve < 0 || curve > ZKB200_BLS12_381_G2) { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
   std::vector<int> devs = device_list();
   const bool multi = devs.size() > 1 && sloc == ZKB200_HOST && ploc == ZKB200_HOST && nmsm >= 1 &&
                      ((nmsm == 1 && (size_t)n >= ((size_t)1 << 16) * devs.size()) || (nmsm >= (int)devs.size()));
   if (multi) {
-    if (curve == ZKB200_BN128) run_multi<Bn254>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out);
-    else run_multi<Bls12381>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out);
+    switch (curve) {
+      case ZKB200_BN128: run_multi<Bn254>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out); break;
+      case ZKB200_BLS12_381: run_multi<Bls12381>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out); break;
+      case ZKB200_BN128_G2: run_multi<Bn254G2>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out); break;
+      default: run_multi<Bls12381G2>(devs, nmsm, (size_t)n, scalars, points, nl, mont, out_mode, window, out); break;
+    }
     return;
   }
   int dev = devs.size() == 1 ? devs[0] : -1;
-  if (curve == ZKB200_BN128) run_on<Bn254>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
-  else run_on<Bls12381>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
+  switch (curve) {
+    case ZKB200_BN128: run_on<Bn254>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
+    case ZKB200_BLS12_381: run_on<Bls12381>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
+    case ZKB200_BN128_G2: run_on<Bn254G2>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
+    default: run_on<Bls12381G2>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
+  }
 }
 
 template <class C>
@@ -676,6 +683,8 @@ void zkb200_sum_points(int curve, int k, const uint64_t* in, int in_mode, int ou
   std::lock_guard<std::mutex> lk(cx.mu);
   if (curve == ZKB200_BN128) run_sum<Bn254>(cx, k, in, in_mode, out_mode, out);
   else if (curve == ZKB200_BLS12_381) run_sum<Bls12381>(cx, k, in, in_mode, out_mode, out);
+  else if (curve == ZKB200_BN128_G2) run_sum<Bn254G2>(cx, k, in, in_mode, out_mode, out);
+  else if (curve == ZKB200_BLS12_381_G2) run_sum<Bls12381G2>(cx, k, in, in_mode, out_mode, out);
   else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
 }
 
@@ -703,6 +712,8 @@ void zkb200_gen_chain(int curve, unsigned long long start, long n, const uint64_
   std::lock_guard<std::mutex> lk(cx.mu);
   if (curve == ZKB200_BN128) run_gen_chain<Bn254>(cx, start, n, p0_affine, d_affine, out, out_loc);
   else if (curve == ZKB200_BLS12_381) run_gen_chain<Bls12381>(cx, start, n, p0_affine, d_affine, out, out_loc);
+  else if (curve == ZKB200_BN128_G2) run_gen_chain<Bn254G2>(cx, start, n, p0_affine, d_affine, out, out_loc);
+  else if (curve == ZKB200_BLS12_381_G2) run_gen_chain<Bls12381G2>(cx, start, n, p0_affine, d_affine, out, out_loc);
   else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
 }
 
@@ -787,6 +798,20 @@ ZK_NTT_SYMBOLS(bls12_381, Bls12381)
 
 ZK_CONVERT_SYMBOLS(bn128, Bn254)
 ZK_CONVERT_SYMBOLS(bls12_381, Bls12381)
+
+// G2 (scope row 8f.3): proj + affine outputs only, like the reference (lib/cbits/curves/g2/proj/bn128_G2_proj.h:43-46)
+#define ZK_REF_SYMBOLS_G2(NAME, ID)                                                                                   \
+  void NAME##_G2_proj_MSM_std_coeff_proj_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {      \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_PROJ, 0, t); }                                     \
+  void NAME##_G2_proj_MSM_mont_coeff_proj_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {     \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 1, OUT_PROJ, 0, t); }                                     \
+  void NAME##_G2_proj_MSM_std_coeff_affine_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {    \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_AFFINE, 0, t); }                                   \
+  void NAME##_G2_proj_MSM_mont_coeff_affine_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {   \
+    msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 1, OUT_AFFINE, 0, t); }
+
+ZK_REF_SYMBOLS_G2(bn128, ZKB200_BN128_G2)
+ZK_REF_SYMBOLS_G2(bls12_381, ZKB200_BLS12_381_G2)
 
 ZK_REF_SYMBOLS(bn128, ZKB200_BN128)
 ZK_REF_SYMBOLS(bls12_381, ZKB200_BLS12_381)
