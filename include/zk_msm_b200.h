@@ -92,6 +92,16 @@ void bls12_381_G2_proj_MSM_mont_coeff_proj_out (int npoints, const uint64_t *exp
 void bls12_381_G2_proj_MSM_std_coeff_affine_out(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
 void bls12_381_G2_proj_MSM_mont_coeff_affine_out(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
 
+/* ---- scope row 8f.4: FFT of G1 group elements (KZG setup, examples/KZG.hs:55), same names and signatures as the
+ * reference (lib/cbits/curves/g1/proj/bn128_G1_proj.h:48-49, definitions bn128_G1_proj.c:678-789 and twin):
+ * src, tgt = 2^m projective points, gen = Montgomery-form generator of the order-2^m subgroup of Fr.
+ * forward: tgt[k] = sum_j gen^(jk) * src[j]; inverse: tgt[j] = 2^-m sum_k gen^(-jk) * src[k]; the results are
+ * normalised ((x, y, 1) / (0, 1, 0)) like the reference's, hence bit-identical. */
+void bn128_G1_proj_fft_forward    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bn128_G1_proj_fft_inverse    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_proj_fft_forward(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_proj_fft_inverse(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+
 /* ---- extensions (not in the reference) -------------------------------------------------------- */
 enum { ZKB200_BN128 = 0, ZKB200_BLS12_381 = 1, ZKB200_BN128_G2 = 2, ZKB200_BLS12_381_G2 = 3 };
 enum { ZKB200_OUT_PROJ = 0, ZKB200_OUT_JAC = 1, ZKB200_OUT_AFFINE = 2, ZKB200_OUT_XYZZ = 3 };

@@ -513,3 +513,39 @@ def test_g2_msm_next_row(zk, curve):
     m = 1 << 11
     want = refs.call_msm(lib, f"{curve}_G2_proj_MSM_mont_coeff_affine_out", sc[:m].ravel(), big[:m].ravel(), W, n=m)
     assert zk.msm(g2, sc[:m], big[:m], mont=True, out="affine").tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_group_fft_next_row(zk, curve):
+    """<curve>_G1_proj_fft_forward / _inverse, bit-identical to the reference C (normalised
+    projective output, lib/cbits/curves/g1/proj/bn128_G1_proj.c:678-789), including infinity entries, repeated
+    points and non-normalised inputs; forward then inverse is the identity on normalised points."""
+    if not refs.have_ref():
+        pytest.skip("needs oracle/_ref")
+    lib = refs.ref()
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    rng = random.Random(12)
+    for m in (0, 1, 2, 3, 5, 7):
+        N = 1 << m
+        gen = np.frombuffer(((_ntt_gen(cv, m) * cv.Rr) % cv.r).to_bytes(32, "little"), dtype=np.uint64).copy()
+        aff = refs.chain_points(curve, N, s0=77, s1=5)
+        if N >= 4:
+            aff[1] = aff[0]                       # repeated point
+            aff[3] = np.uint64(0xFFFFFFFFFFFFFFFF)  # infinity
+        proj = zk.batch_from_affine(curve, aff, "proj")
+        if N >= 8:                                # a non-normalised representative: (xz, yz, z)
+            z = rng.randrange(2, cv.p)
+            P = cv.affine_from_bytes(aff[5].tobytes())
+            proj[5] = np.frombuffer(cv.fp_to_bytes(P[0] * z % cv.p) + cv.fp_to_bytes(P[1] * z % cv.p) + cv.fp_to_bytes(z), dtype=np.uint64)
+        for inverse in (False, True):
+            f = getattr(lib, f"{curve}_G1_proj_fft_{'inverse' if inverse else 'forward'}")
+            f.argtypes = [ctypes.c_int, refs.U64P, refs.U64P, refs.U64P]
+            f.restype = None
+            want = np.zeros_like(proj)
+            f(m, refs.ptr(gen), refs.ptr(np.ascontiguousarray(proj).ravel()), refs.ptr(want.ravel()))
+            got = zk.group_fft(curve, m, gen, proj, inverse=inverse)
+            assert got.tobytes() == want.tobytes(), (m, inverse)
+        fwd = zk.group_fft(curve, m, gen, proj)
+        back = zk.group_fft(curve, m, gen, fwd, inverse=True)
+        assert zk.batch_to_affine(curve, back, "proj").tobytes() == aff.tobytes(), m

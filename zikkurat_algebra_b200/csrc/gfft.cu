@@ -1,0 +1,133 @@
+// FFT of G1 group elements -- scope row 8f.4 (KZG setup: examples/KZG.hs:55, lib/src/.../G1/Affine.hs:152-157).
+// Same semantics as the reference's recursive routines
+//   <curve>_G1_proj_fft_forward / _inverse      lib/cbits/curves/g1/proj/bn128_G1_proj.c:678-789
+//   forward:  tgt[k] = sum_j gen^(j*k) * src[j]            inverse:  tgt[j] = N^-1 * sum_k gen^(-j*k) * src[k]
+// on N = 2^m projective points, natural order in and out, results NORMALISED ((x, y, 1) or the infinity (0, 1, 0)
+// exactly like bn128_G1_proj_normalize, :75-96), hence bit-comparable.
+//
+// Radix-2 decimation in time on XYZZ points held in global memory: one launch per stage, one thread per butterfly
+// (a, b) -> (a + w*b, a - w*b); w*b is a 4-bit fixed-window scalar multiplication (the reference does the same per
+// butterfly with bn128_G1_proj_scl_Fr_mont).  Twiddles come from the Fr table of ntt.cu (w^-i = -w^(N/2-i)).
+// The work is N/2 * log2 N scalar multiplications (~3 300 Fp multiplications each): IMAD-bound, no data reuse to stage.
+#include <cuda_runtime.h>
+
+#include "gfft.cuh"
+#include "msm_common.cuh"
+#include "ntt.cuh"
+
+namespace zk {
+
+// one out-of-line copy of each group operation for this translation unit
+template <class P>
+__device__ __noinline__ void gf_add(Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add<P>(a, b); }
+template <class P>
+__device__ __noinline__ void gf_dbl(Xyzz<P>& a) { a = xyzz_dbl<P>(a); }
+
+// k * p for a standard-form 256-bit scalar k (8 x u32), 4-bit fixed windows, table of 1p..15p in local memory
+template <class P>
+__device__ __noinline__ Xyzz<P> xyzz_scalar_mul(const Xyzz<P>& p, const uint32_t* k) {
+  Xyzz<P> tab[15];
+  tab[0] = p;
+  for (int i = 1; i < 15; i++) {           // tab[i] = (i+1) * p
+    if (i & 1) { tab[i] = tab[i >> 1]; gf_dbl<P>(tab[i]); }
+    else { tab[i] = tab[i - 1]; gf_add<P>(tab[i], p); }
+  }
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int w = 63; w >= 0; w--) {
+    for (int d = 0; d < 4; d++) gf_dbl<P>(acc);   // no-op while acc is infinity
+    uint32_t dig = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+    if (dig) gf_add<P>(acc, tab[dig - 1]);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ size_t gfft_bitrev(size_t x, int bits) {
+  return bits == 0 ? 0 : (size_t)(__brevll((unsigned long long)x) >> (64 - bits));
+}
+
+// projective (X:Y:Z) records -> XYZZ, written to the bit-reversed position
+template <class C>
+__global__ void __launch_bounds__(128) k_gfft_load(const uint32_t* __restrict__ src, int m, XyzzMem<typename C::Fp>* __restrict__ dst) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((size_t)1 << m)) return;
+  const uint32_t* s = src + i * 3 * L;
+  Fe<P> X, Y, Z;
+  for (int k = 0; k < L; k++) { X.l[k] = s[k]; Y.l[k] = s[L + k]; Z.l[k] = s[2 * L + k]; }
+  store_xyzz<P>(dst + gfft_bitrev(i, m), xyzz_from_proj<P>(X, Y, Z));
+}
+
+// stage s (1-based): butterflies at distance 2^(s-1) inside blocks of 2^s
+template <class C>
+__global__ void __launch_bounds__(128)
+k_gfft_stage(XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restrict__ table, int m, int s, int inverse) {
+  using P = typename C::Fp;
+  using F = typename C::Fr;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t half = (size_t)1 << (m - 1);
+  if (t >= half) return;
+  const size_t j = t & (((size_t)1 << (s - 1)) - 1);
+  const size_t ia = ((t >> (s - 1)) << s) + j, ib = ia + ((size_t)1 << (s - 1));
+  const size_t idx = j << (m - s);
+  Xyzz<P> a = load_xyzz<P>(data + ia), b = load_xyzz<P>(data + ib);
+  if (idx != 0) {
+    Fe<F> w;
+    const uint32_t* tw = table + (inverse ? (half - idx) : idx) * 8;
+    for (int k = 0; k < 8; k++) w.l[k] = tw[k];
+    if (inverse) w = fe_neg<F>(w);                 // w^-idx = -w^(N/2 - idx)
+    w = fe_from_mont<F>(w);                        // plain integer for the scalar multiplication
+    b = xyzz_scalar_mul<P>(b, w.l);
+  }
+  Xyzz<P> nb = b;
+  nb.Y = fe_neg<P>(b.Y);
+  gf_add<P>(nb, a);
+  gf_add<P>(a, b);
+  store_xyzz<P>(data + ia, a);
+  store_xyzz<P>(data + ib, nb);
+}
+
+// optional scaling by N^-1 (inverse transform), then normalised projective output
+template <class C>
+__global__ void __launch_bounds__(128)
+k_gfft_store(const XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restrict__ table, int m, int scale,
+             uint32_t* __restrict__ dst) {
+  using P = typename C::Fp;
+  using F = typename C::Fr;
+  constexpr int L = P::L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((size_t)1 << m)) return;
+  Xyzz<P> a = load_xyzz<P>(data + i);
+  if (scale && m > 0) {
+    Fe<F> ninv;
+    const uint32_t* q = table + ((size_t)1 << (m - 1)) * 8;
+    for (int k = 0; k < 8; k++) ninv.l[k] = q[k];
+    ninv = fe_from_mont<F>(ninv);
+    a = xyzz_scalar_mul<P>(a, ninv.l);
+  }
+  uint32_t* o = dst + i * 3 * L;
+  Affine<P> aff;
+  if (xyzz_to_affine<P>(a, aff)) {
+    for (int k = 0; k < L; k++) { o[k] = aff.x.l[k]; o[L + k] = aff.y.l[k]; o[2 * L + k] = P::one(k); }
+  } else {
+    for (int k = 0; k < L; k++) { o[k] = 0; o[L + k] = P::one(k); o[2 * L + k] = 0; }
+  }
+}
+
+template <class C>
+void gfft_device(cudaStream_t s, int m, const uint32_t* d_gen, const uint32_t* d_src, void* d_work, uint32_t* d_table,
+                 uint32_t* d_dst, int inverse) {
+  using Mem = XyzzMem<typename C::Fp>;
+  const size_t N = (size_t)1 << m;
+  Mem* data = (Mem*)d_work;
+  ntt_build_table<typename C::Fr>(s, d_gen, N >> 1, m, d_table);
+  k_gfft_load<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(d_src, m, data);
+  for (int st = 1; st <= m; st++)
+    k_gfft_stage<C><<<(unsigned)(((N >> 1) + 127) / 128), 128, 0, s>>>(data, d_table, m, st, inverse);
+  k_gfft_store<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(data, d_table, m, inverse, d_dst);
+}
+
+template void gfft_device<Bn254>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int);
+template void gfft_device<Bls12381>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int);
+
+}  // namespace zk

@@ -139,12 +139,19 @@ k_ntt_pass(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const ui
 }
 
 template <class F>
+void ntt_build_table(cudaStream_t s, const uint32_t* d_gen, size_t half, int m, uint32_t* d_table) {
+  size_t tthreads = ((half ? half : 1) + 31) / 32;
+  k_ntt_table<F><<<(unsigned)((tthreads + 127) / 128), 128, 0, s>>>(d_gen, half, m, d_table);
+}
+template void ntt_build_table<Bn254Fr>(cudaStream_t, const uint32_t*, size_t, int, uint32_t*);
+template void ntt_build_table<Bls12381Fr>(cudaStream_t, const uint32_t*, size_t, int, uint32_t*);
+
+template <class F>
 void ntt_device(cudaStream_t s, int m, const uint32_t* d_gen, const uint32_t* d_src, uint32_t* d_tmp, uint32_t* d_dst,
                 uint32_t* d_table, int inverse) {
   const size_t N = (size_t)1 << m;
   const size_t half = N >> 1;
-  size_t tthreads = ((half ? half : 1) + 31) / 32;
-  k_ntt_table<F><<<(unsigned)((tthreads + 127) / 128), 128, 0, s>>>(d_gen, half, m, d_table);
+  ntt_build_table<F>(s, d_gen, half, m, d_table);
   if (m == 0) {
     cudaMemcpyAsync(d_dst, d_src, 32, cudaMemcpyDeviceToDevice, s);
     return;

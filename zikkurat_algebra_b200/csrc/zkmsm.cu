@@ -16,6 +16,7 @@
 
 #include "../../include/zk_msm_b200.h"
 #include "msm_common.cuh"
+#include "gfft.cuh"
 #include "ntt.cuh"
 #include "sort.cuh"
 
@@ -666,6 +667,30 @@ void run_ntt(int m, const uint64_t* gen, const uint64_t* src, int src_loc, uint6
   CK(cudaStreamSynchronize(s));
 }
 
+// FFT of G1 group elements (scope row 8f.4): host buffers in, host buffers out
+template <class C>
+void run_gfft(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, int inverse) {
+  constexpr int L = C::Fp::L;
+  if (m < 0 || m > 26) { fprintf(stderr, "[zkmsm_b200] fatal: group FFT size 2^%d unsupported\n", m); abort(); }
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  const size_t N = (size_t)1 << m, bytes = N * 3 * L * 4;
+  uint32_t* d_src = (uint32_t*)cx.ensure(B_POINTS, bytes);
+  uint32_t* d_dst = (uint32_t*)cx.ensure(B_KEYS0, bytes);
+  void* d_work = cx.ensure(B_BUCKETS, N * sizeof(XyzzMem<typename C::Fp>));
+  uint32_t* d_table = (uint32_t*)cx.ensure(B_NTT_TABLE, (N / 2 + 1) * 32);
+  uint32_t* d_gen = (uint32_t*)cx.ensure(B_OUT, 4096);
+  cudaStream_t s = cx.s_main;
+  CK(cudaMemcpyAsync(d_gen, gen, 32, cudaMemcpyHostToDevice, s));
+  host_to_device(cx, d_src, src, bytes, s);
+  g_launches += 3 + m;
+  gfft_device<C>(s, m, d_gen, d_src, d_work, d_table, d_dst, inverse);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+}
+
 }  // namespace
 
 // ---- exported C ABI -----------------------------------------------------------------------------------
@@ -792,6 +817,15 @@ const char* zkb200_version(void) { return "zkmsm_b200 0.1 (sm_100a)"; }
     run_ntt<CURVE::Fr>(m, gen, src, ZKB200_HOST, tgt, ZKB200_HOST, 0); }                                                                        \
   void NAME##_poly_mont_ntt_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                 \
     run_ntt<CURVE::Fr>(m, gen, src, ZKB200_HOST, tgt, ZKB200_HOST, 1); }
+
+#define ZK_GFFT_SYMBOLS(NAME, CURVE)                                                                                  \
+  void NAME##_G1_proj_fft_forward(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                   \
+    run_gfft<CURVE>(m, gen, src, tgt, 0); }                                                                           \
+  void NAME##_G1_proj_fft_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                   \
+    run_gfft<CURVE>(m, gen, src, tgt, 1); }
+
+ZK_GFFT_SYMBOLS(bn128, Bn254)
+ZK_GFFT_SYMBOLS(bls12_381, Bls12381)
 
 ZK_NTT_SYMBOLS(bn128, Bn254)
 ZK_NTT_SYMBOLS(bls12_381, Bls12381)
