@@ -237,6 +237,17 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     if (c < 1) c = 1;
     if (c > 24) c = 24;
     W = signed_windows(nbits, c);
+    if ((long long)nmsm * W > 65535) {
+      // segments are a grid dimension (<= 65535): very large batches are processed in sub-batches
+      int sub = 65535 / W;
+      const int out_c = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
+      for (int m0 = 0; m0 < nmsm; m0 += sub) {
+        int cntm = nmsm - m0 < sub ? nmsm - m0 : sub;
+        run_msm<C>(cx, cntm, n, scalars + (size_t)m0 * n * nl, sloc, points, ploc, nl, mont, out_mode, c,
+                   out + (size_t)m0 * out_c * (L / 2));
+      }
+      return;
+    }
     const uint32_t NB = 1u << (c - 1);
     const int nseg = nmsm * W;
     st.c = c; st.W = W; st.insertions = (long long)nseg * (long long)n;
