@@ -270,6 +270,17 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     size_t lo[MAX_SLICES + 1];
     size_t nmax = 0;
     for (int k = 0; k <= K; k++) lo[k] = (n * (size_t)k / K) & ~(size_t)3;   // multiples of 4 keep 16-byte alignment
+    if (K == 2) {
+      // the first slice is what nothing can hide: make it the smaller one, as long as its accumulation still
+      // covers the transfer of the rest ($ZKB200_SLICE0 = percent of the points in slice 0)
+      const char* e = getenv("ZKB200_SLICE0");
+      // accumulate time of slice 0 must cover the PCIe time of slice 1: f >= t/(a+t) with a = accumulate and
+      // t = transfer time per point (measured: BN254 ~1.9/1.9 us per 1000 points, BLS12-381 5.4/2.6, G2 heavier)
+      int pct = e ? atoi(e) : (L <= 8 ? 50 : (L <= 12 ? 33 : 25));
+      if (pct < 5) pct = 5;
+      if (pct > 95) pct = 95;
+      lo[1] = (n * (size_t)pct / 100) & ~(size_t)3;
+    }
     lo[K] = n;
     for (int k = 0; k < K; k++) if (lo[k + 1] - lo[k] > nmax) nmax = lo[k + 1] - lo[k];
 
