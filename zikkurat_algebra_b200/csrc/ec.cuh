@@ -187,6 +187,32 @@ ZK_HD Xyzz<P> xyzz_add(const Xyzz<P>& a, const Xyzz<P>& b) {
   return r;
 }
 
+// add-2008-s with every multiplication out of line (same arithmetic, small code / fewer registers)
+template <class P>
+ZK_HD Xyzz<P> xyzz_add_calls(const Xyzz<P>& a, const Xyzz<P>& b) {
+  if (xyzz_is_inf<P>(a)) return b;
+  if (xyzz_is_inf<P>(b)) return a;
+  Fe<P> U1 = fe_mul_call<P>(a.X, b.ZZ);
+  Fe<P> U2 = fe_mul_call<P>(b.X, a.ZZ);
+  Fe<P> S1 = fe_mul_call<P>(a.Y, b.ZZZ);
+  Fe<P> S2 = fe_mul_call<P>(b.Y, a.ZZZ);
+  Fe<P> Pd = fe_sub<P>(U2, U1);
+  Fe<P> R = fe_sub<P>(S2, S1);
+  if (fe_is_zero<P>(Pd)) {
+    if (fe_is_zero<P>(R)) return xyzz_dbl<P>(a);
+    return xyzz_inf<P>();
+  }
+  Xyzz<P> r;
+  Fe<P> PP = fe_sqr_call<P>(Pd);
+  Fe<P> PPP = fe_mul_call<P>(Pd, PP);
+  Fe<P> Q = fe_mul_call<P>(U1, PP);
+  r.X = fe_sub<P>(fe_sub<P>(fe_sub<P>(fe_sqr_call<P>(R), PPP), Q), Q);
+  r.Y = fe_mul2_call<P>(R, fe_sub<P>(Q, r.X), fe_neg<P>(S1), PPP);
+  r.ZZ = fe_mul_call<P>(fe_mul_call<P>(a.ZZ, b.ZZ), PP);
+  r.ZZZ = fe_mul_call<P>(fe_mul_call<P>(a.ZZZ, b.ZZZ), PPP);
+  return r;
+}
+
 template <class P>
 ZK_HD Affine<P> affine_neg(const Affine<P>& p) {
   Affine<P> r;

@@ -40,6 +40,8 @@ __device__ __forceinline__ void xyzz_dbl_tm(const Team& tm, Xyzz<P>& a) {
 // Level 1 reads the buckets (U = V = B, M = 1, weights t+1) with the classic running sum over m buckets.
 // With K input slices (H2D overlap, see run_msm) there are K bucket arrays `slice_stride` apart; their
 // sum is taken on the fly: run += B_0[i] + ... + B_{K-1}[i] through the same addition site.
+// 12-limb fields: out-of-line multiplications (250 -> ~170 registers, 3 CTAs per SM); 8 limbs: inlined
+#define RF_ADD(x, y) (P::L > 8 ? xyzz_add_calls<P>((x), (y)) : xyzz_add<P>((x), (y)))
 template <class C>
 __global__ void __launch_bounds__(128)
 k_reduce_first(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices, size_t slice_stride, size_t total_out,
@@ -51,8 +53,8 @@ k_reduce_first(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices,
   Xyzz<P> run = xyzz_inf<P>(), acc = xyzz_inf<P>();
   for (int i = (1 << log_m) - 1; i >= 0; i--) {
 #pragma unroll 1
-    for (int k = 0; k < nslices; k++) run = xyzz_add<P>(run, load_xyzz<P>(b + (size_t)k * slice_stride + i));
-    acc = xyzz_add<P>(acc, run);
+    for (int k = 0; k < nslices; k++) run = RF_ADD(run, load_xyzz<P>(b + (size_t)k * slice_stride + i));
+    acc = RF_ADD(acc, run);
   }
   store_xyzz<P>(U + t, acc);
   store_xyzz<P>(V + t, run);
