@@ -39,7 +39,7 @@ PRODUCTS_PER_INSERTION = {"bn128": 1360, "bls12_381": 3000}   # 10 Fp mul x (2L^
 EXECUTED_PER_INSERTION = {"bn128": 6 * 136 + 2 * 108 + 200, "bls12_381": 6 * 300 + 2 * 234 + 444}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_accumulate launch from an `ncu --set full` capture
 # (profiles/*_ncu_k_accumulate_*.txt), keyed by (curve, log2 n); None where no capture exists.
-NCU_TRAFFIC = {("bls12_381", 20): 1.739097e9 + 0.169035e9}   # profiles/r1_d_ncu_k_accumulate_bls12381_2p20.txt
+NCU_TRAFFIC = {("bls12_381", 20): 1.738798e9 + 0.172671e9}   # profiles/r1_e_ncu_k_accumulate_bls12381_2p20.txt
 METRIC = "G1 MSM throughput"
 UNIT = "points/s"
 

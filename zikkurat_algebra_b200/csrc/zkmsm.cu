@@ -143,12 +143,16 @@ DeviceCtx& get_ctx(int d = -1) {
 // ring of pinned buffers and each chunk is sent with an async DMA as soon as it is staged, so the host-side
 // copy runs at several threads' memory bandwidth and overlaps with the PCIe transfer.  Pinned (registered)
 // source memory skips all that and is sent directly.  Returns when every chunk has been queued on `stream`.
+bool host_is_pinned(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+  (void)cudaGetLastError();
+  return false;
+}
+
 void host_to_device(DeviceCtx& cx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
   if (bytes == 0) return;
-  cudaPointerAttributes attr;
-  bool pinned = false;
-  if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
-  else (void)cudaGetLastError();
+  const bool pinned = host_is_pinned(src);
   if (pinned || bytes < ((size_t)2 << 20) || getenv("ZKB200_NO_STAGING")) {
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     return;
@@ -276,7 +280,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       const char* e = getenv("ZKB200_SLICE0");
       // accumulate time of slice 0 must cover the PCIe time of slice 1: f >= t/(a+t) with a = accumulate and
       // t = transfer time per point (measured: BN254 ~1.9/1.9 us per 1000 points, BLS12-381 5.4/2.6, G2 heavier)
-      int pct = e ? atoi(e) : (L <= 8 ? 50 : (L <= 12 ? 33 : 25));
+      // Ordinary (pageable) memory goes through the staging ring at about half the PCIe rate, so t doubles.
+      const bool pinned = host_is_pinned(points);
+      int pct = e ? atoi(e) : (pinned ? (L <= 8 ? 50 : (L <= 12 ? 33 : 25)) : (L <= 12 ? 50 : 35));   // measured (profiles/r1_notes.md)
       if (pct < 5) pct = 5;
       if (pct > 95) pct = 95;
       lo[1] = (n * (size_t)pct / 100) & ~(size_t)3;
