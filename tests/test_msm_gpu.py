@@ -560,3 +560,20 @@ def test_very_large_batch_is_split(zk):
     for i in (0, 1, 511, 512, 1499):
         assert got[i].tobytes() == cpu_affine(curve, sc[i], pts).tobytes(), i
     assert zk.last_stats()["nwindows"] * nmsm > 65535
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_unreduced_montgomery_scalars(zk, curve):
+    """mont_coeff inputs >= r (not canonical): the reference's REDC still decodes them; so must we."""
+    n = 64
+    pts = refs.chain_points(curve, n)
+    rng = np.random.Generator(np.random.PCG64(5))
+    sc = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64, endpoint=False)   # full 256-bit values, most >= r
+    sc[0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    cv = pyec.CURVES[curve]
+    sc[1] = np.frombuffer(cv.r.to_bytes(32, "little"), dtype=np.uint64)            # exactly r  -> 0
+    sc[2] = np.frombuffer((cv.r + 1).to_bytes(32, "little"), dtype=np.uint64)
+    want = cpu_affine(curve, sc, pts, "mont")
+    for rep in ("proj", "jac"):
+        got = zk.call_reference_symbol(f"{curve}_G1_{rep}_MSM_mont_coeff_affine_out", sc, pts)
+        assert got.tobytes() == want.tobytes(), rep
