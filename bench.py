@@ -73,6 +73,7 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.marks = {}
 
     def start(self):
         try:
@@ -86,7 +87,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self, name):
+        self.marks[name] = time.time()
 
     def stop(self):
         if not self.proc:
@@ -98,7 +102,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0, t1 = self.marks.get("t0", 0.0), self.marks.get("t1", float("inf"))
+        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.05]
+        for ln in (inside if inside else [ln for (_, ln) in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -249,13 +255,15 @@ def main():
             ms = float(t.item())
         return ms, res, acc_ms, sort_ms, stats
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                      # nvidia-smi needs ~0.1 s to deliver its first sample: start before the warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_device()
     launches0 = zk.launch_count()
+    sampler.mark("t0")
     ms_dev, res_dev, acc_ms, sort_ms, stats = timed(step_device, args.steps, collect_stats=True)
+    sampler.mark("t1")
     launches = zk.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
