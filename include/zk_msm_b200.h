@@ -132,6 +132,12 @@ void zkb200_gen_chain(int curve, unsigned long long start, long n, const uint64_
 void zkb200_ntt(int curve, int m, const uint64_t *gen, const uint64_t *src, int src_loc, uint64_t *tgt, int tgt_loc,
                 int inverse);
 
+/* Resident inputs without writing any CUDA code: copy a host buffer (e.g. the SRS of a KZG prover, which is the same
+ * for every commitment: examples/KZG.hs:77-88) to the selected device once and pass the returned pointer to
+ * zkb200_msm / zkb200_ntt with location ZKB200_DEVICE.  Free it with zkb200_device_free. */
+void *zkb200_device_upload(const void *host, size_t bytes);
+void zkb200_device_free(void *device_ptr);
+
 /* Number of kernels this library has launched since it was loaded (bench.py's "gpu_launches"). */
 long long zkb200_launch_count(void);
 

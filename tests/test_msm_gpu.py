@@ -577,3 +577,20 @@ def test_unreduced_montgomery_scalars(zk, curve):
     for rep in ("proj", "jac"):
         got = zk.call_reference_symbol(f"{curve}_G1_{rep}_MSM_mont_coeff_affine_out", sc, pts)
         assert got.tobytes() == want.tobytes(), rep
+
+
+def test_resident_srs_repeated_commits(zk):
+    """KZG prover shape: the SRS is uploaded once (zkb200_device_upload), every commitment sends only scalars."""
+    curve, n = "bn128", 1 << 12
+    srs = refs.chain_points(curve, n)
+    res = zk.ResidentPoints(curve, srs)
+    try:
+        for i in range(3):
+            sc = refs.random_scalars(curve, n, seed=600 + i)
+            assert res.msm(sc, mont=True).tobytes() == cpu_affine(curve, sc, srs, "mont").tobytes()
+        batch = np.stack([refs.random_scalars(curve, n, seed=700 + i) for i in range(4)])
+        got = res.msm(batch, mont=True)
+        for i in range(4):
+            assert got[i].tobytes() == cpu_affine(curve, batch[i], srs, "mont").tobytes()
+    finally:
+        res.close()

@@ -20,7 +20,7 @@ import numpy as np
 
 __all__ = [
     "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "G2_SYMBOLS", "GFFT_SYMBOLS", "group_fft", "call_reference_symbol",
-    "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
+    "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "ResidentPoints", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -46,7 +46,7 @@ NTT_SYMBOLS = [f"{c}_poly_mont_ntt_{d}" for c in ("bn128", "bls12_381") for d in
 G2_SYMBOLS = [f"{c}_G2_proj_MSM_{f}_coeff_{o}_out" for c in ("bn128", "bls12_381") for f in ("std", "mont") for o in ("proj", "affine")]
 GFFT_SYMBOLS = [f"{c}_G1_proj_fft_{d}" for c in ("bn128", "bls12_381") for d in ("forward", "inverse")]
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
-                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt"]
+                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt", "zkb200_device_upload", "zkb200_device_free"]
 
 _U64P = ctypes.POINTER(ctypes.c_uint64)
 _lib: Optional[ctypes.CDLL] = None
@@ -86,6 +86,10 @@ def lib() -> ctypes.CDLL:
         L.zkb200_ntt.argtypes = [ctypes.c_int, ctypes.c_int, _U64P, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                  ctypes.c_int]
         L.zkb200_ntt.restype = None
+        L.zkb200_device_upload.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+        L.zkb200_device_upload.restype = ctypes.c_void_p
+        L.zkb200_device_free.argtypes = [ctypes.c_void_p]
+        L.zkb200_device_free.restype = None
         for name in NTT_SYMBOLS + GFFT_SYMBOLS:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P]
@@ -250,6 +254,37 @@ def gen_chain(curve: str, n: int, p0: np.ndarray, d: np.ndarray, start: int = 0,
     out = np.zeros((n, 2 * cv["nlimbs_p"]), dtype=np.uint64)
     lib().zkb200_gen_chain(cv["id"], start, n, _ptr(p0), _ptr(d), out.ctypes.data, HOST)
     return out
+
+
+class ResidentPoints:
+    """A point array kept on the device across calls (the SRS of a KZG prover): upload once, commit many times."""
+
+    def __init__(self, curve: str, points: np.ndarray):
+        p = _as_u64(points)
+        self.curve, self.n = curve, p.shape[0]
+        self.ptr = lib().zkb200_device_upload(p.ctypes.data, p.nbytes)
+
+    def msm(self, scalars: np.ndarray, mont: bool = True, out: str = "affine", window: int = 0) -> np.ndarray:
+        """scalars: (n, 4) or (nmsm, n, 4) host array -> one result per MSM."""
+        cv = CURVES[self.curve]
+        s = _as_u64(scalars)
+        batch = s.reshape(-1, self.n, 4)
+        mode = _OUT[out]
+        res = np.zeros((batch.shape[0], _OUT_COORDS[mode] * cv["nlimbs_p"]), dtype=np.uint64)
+        lib().zkb200_msm(cv["id"], batch.shape[0], self.n, batch.ctypes.data, HOST, self.ptr, DEVICE, 4, int(mont), mode, window,
+                         _ptr(res))
+        return res if s.ndim == 3 else res[0]
+
+    def close(self) -> None:
+        if self.ptr:
+            lib().zkb200_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def launch_count() -> int:

@@ -753,6 +753,25 @@ void zkb200_set_devices(const int* devices, int count) {
 
 long long zkb200_launch_count(void) { return g_launches.load(); }
 
+void* zkb200_device_upload(const void* host, size_t bytes) {
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  void* d = nullptr;
+  CK(cudaMalloc(&d, bytes ? bytes : 1));
+  host_to_device(cx, d, host, bytes, cx.s_copy);
+  CK(cudaStreamSynchronize(cx.s_copy));
+  return d;
+}
+
+void zkb200_device_free(void* device_ptr) {
+  if (!device_ptr) return;
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  CK(cudaFree(device_ptr));
+}
+
 void zkb200_ntt(int curve, int m, const uint64_t* gen, const uint64_t* src, int src_loc, uint64_t* tgt, int tgt_loc, int inverse) {
   if (curve == ZKB200_BN128) run_ntt<Bn254Fr>(m, gen, src, src_loc, tgt, tgt_loc, inverse);
   else if (curve == ZKB200_BLS12_381) run_ntt<Bls12381Fr>(m, gen, src, src_loc, tgt, tgt_loc, inverse);
