@@ -101,6 +101,27 @@ void bn128_G1_proj_fft_forward    (int m, const uint64_t *gen, const uint64_t *s
 void bn128_G1_proj_fft_inverse    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
 void bls12_381_G1_proj_fft_forward(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
 void bls12_381_G1_proj_fft_inverse(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+/* the Jacobian-input and G2 twins (lib/cbits/curves/g1/jac/bn128_G1_jac.h:48-49, .../g2/proj/bn128_G2_proj.h:48-49) */
+void bn128_G1_jac_fft_forward     (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bn128_G1_jac_fft_inverse     (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_jac_fft_forward (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G1_jac_fft_inverse (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bn128_G2_proj_fft_forward    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bn128_G2_proj_fft_inverse    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G2_proj_fft_forward(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G2_proj_fft_inverse(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
+/* G2 batch conversions (lib/cbits/curves/g2/proj/bn128_G2_proj.h:9-10) */
+void bn128_G2_proj_batch_to_affine      (int N, const uint64_t *src, uint64_t *tgt);
+void bn128_G2_proj_batch_from_affine    (int N, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G2_proj_batch_to_affine  (int N, const uint64_t *src, uint64_t *tgt);
+void bls12_381_G2_proj_batch_from_affine(int N, const uint64_t *src, uint64_t *tgt);
+/* the exported-but-unused slow MSM variants (bn128_G1_proj.c:610-619; header name misspelt at bn128_G1_proj.h:47) */
+void bn128_G1_proj_MSM_std_coeff_proj_out_slow_reference    (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G1_jac_MSM_std_coeff_jac_out_slow_reference      (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bn128_G2_proj_MSM_std_coeff_proj_out_slow_reference    (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_proj_MSM_std_coeff_proj_out_slow_reference(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G1_jac_MSM_std_coeff_jac_out_slow_reference  (int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
+void bls12_381_G2_proj_MSM_std_coeff_proj_out_slow_reference(int npoints, const uint64_t *expos, const uint64_t *grps, uint64_t *tgt, int expo_nlimbs);
 
 /* ---- extensions (not in the reference) -------------------------------------------------------- */
 enum { ZKB200_BN128 = 0, ZKB200_BLS12_381 = 1, ZKB200_BN128_G2 = 2, ZKB200_BLS12_381_G2 = 3 };

@@ -20,7 +20,7 @@ def test_library_builds_and_exports_declared_symbols():
     assert len(declared) >= 26
     for name in declared:
         assert hasattr(lib, name), f"missing export {name}"
-    assert declared == set(zk.REFERENCE_SYMBOLS) | set(zk.EXTENSION_SYMBOLS) | set(zk.CONVERT_SYMBOLS) | set(zk.NTT_SYMBOLS) | set(zk.G2_SYMBOLS) | set(zk.GFFT_SYMBOLS)
+    assert declared == set(zk.REFERENCE_SYMBOLS) | set(zk.EXTENSION_SYMBOLS) | set(zk.CONVERT_SYMBOLS) | set(zk.NTT_SYMBOLS) | set(zk.G2_SYMBOLS) | set(zk.GFFT_SYMBOLS) | set(zk.EXTRA_SYMBOLS)
 
 
 def test_no_oracle_in_product():

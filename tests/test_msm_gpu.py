@@ -594,3 +594,69 @@ def test_resident_srs_repeated_commits(zk):
             assert got[i].tobytes() == cpu_affine(curve, batch[i], srs, "mont").tobytes()
     finally:
         res.close()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_remaining_twins_of_the_next_rows(zk, curve):
+    """Jacobian-input and G2 group FFTs, G2 batch conversions and the *_slow_reference MSM symbols: the rest of the
+    symbol families around scope rows 8f.1/8f.3/8f.4, each against the reference C."""
+    if not refs.have_ref():
+        pytest.skip("needs oracle/_ref")
+    lib = refs.ref()
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    m = 4
+    N = 1 << m
+    gen = np.frombuffer(((_ntt_gen(cv, m) * cv.Rr) % cv.r).to_bytes(32, "little"), dtype=np.uint64).copy()
+
+    def ref_fft(sym, arr):
+        f = getattr(lib, sym)
+        f.argtypes = [ctypes.c_int, refs.U64P, refs.U64P, refs.U64P]
+        f.restype = None
+        out = np.zeros_like(arr)
+        f(m, refs.ptr(gen), refs.ptr(np.ascontiguousarray(arr).ravel()), refs.ptr(out.ravel()))
+        return out
+
+    # G1, Jacobian input
+    aff = refs.chain_points(curve, N, s0=31, s1=7)
+    aff[2] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    jac = zk.batch_from_affine(curve, aff, "jac")
+    for inverse in (False, True):
+        want = ref_fft(f"{curve}_G1_jac_fft_{'inverse' if inverse else 'forward'}", jac)
+        assert zk.group_fft(curve, m, gen, jac, inverse=inverse, group="G1_jac").tobytes() == want.tobytes(), inverse
+    # G2: conversions and FFT
+    W = 4 * L
+    g2aff = _g2_ref_chain(curve, N)
+    g2aff[1] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    conv = getattr(lib, f"{curve}_G2_proj_batch_from_affine")
+    conv.argtypes = [ctypes.c_int, refs.U64P, refs.U64P]
+    conv.restype = None
+    g2proj = np.zeros((N, 6 * L), np.uint64)
+    conv(N, refs.ptr(g2aff.ravel()), refs.ptr(g2proj.ravel()))
+    mine = np.zeros_like(g2proj)
+    f = getattr(zk.lib(), f"{curve}_G2_proj_batch_from_affine")
+    f(N, refs.ptr(g2aff.ravel()), refs.ptr(mine.ravel()))
+    assert mine.tobytes() == g2proj.tobytes()
+    back = np.zeros_like(g2aff)
+    getattr(zk.lib(), f"{curve}_G2_proj_batch_to_affine")(N, refs.ptr(g2proj.ravel()), refs.ptr(back.ravel()))
+    assert back.tobytes() == g2aff.tobytes()
+    for inverse in (False, True):
+        want = ref_fft(f"{curve}_G2_proj_fft_{'inverse' if inverse else 'forward'}", g2proj)
+        assert zk.group_fft(curve, m, gen, g2proj, inverse=inverse, group="G2_proj").tobytes() == want.tobytes(), inverse
+    # slow_reference symbols: same group element as the reference's slow routine
+    n = 25
+    pts = refs.chain_points(curve, n)
+    sc = refs.random_scalars(curve, n, seed=3, reduce=False)
+    want_aff = cpu_affine(curve, sc, pts)
+    for rep in ("proj", "jac"):
+        sym = f"{curve}_G1_{rep}_MSM_std_coeff_{rep}_out_slow_reference"
+        ref_out = refs.call_msm(lib, sym, sc.ravel(), pts.ravel(), 3 * L, n=n)
+        assert refs.call2(lib, f"{curve}_G1_{rep}_to_affine", ref_out, 2 * L).tobytes() == want_aff.tobytes()
+        got = zk.call_reference_symbol(sym, sc, pts)
+        assert refs.call2(lib, f"{curve}_G1_{rep}_to_affine", got, 2 * L).tobytes() == want_aff.tobytes()
+    g2pts = _g2_ref_chain(curve, n)
+    sym = f"{curve}_G2_proj_MSM_std_coeff_proj_out_slow_reference"
+    ref_out = refs.call_msm(lib, sym, sc.ravel(), g2pts.ravel(), 6 * L, n=n)
+    got = zk.call_reference_symbol(sym, sc, g2pts)
+    assert (refs.call2(lib, f"{curve}_G2_proj_to_affine", got, W).tobytes()
+            == refs.call2(lib, f"{curve}_G2_proj_to_affine", ref_out, W).tobytes())

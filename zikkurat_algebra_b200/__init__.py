@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 __all__ = [
-    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "G2_SYMBOLS", "GFFT_SYMBOLS", "group_fft", "call_reference_symbol",
+    "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "G2_SYMBOLS", "GFFT_SYMBOLS", "EXTRA_SYMBOLS", "group_fft", "call_reference_symbol",
     "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "ResidentPoints", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
 ]
 
@@ -44,7 +44,10 @@ REFERENCE_SYMBOLS = [
 CONVERT_SYMBOLS = [f"{c}_G1_{r}_batch_{d}_affine" for c in ("bn128", "bls12_381") for r in ("proj", "jac") for d in ("to", "from")]
 NTT_SYMBOLS = [f"{c}_poly_mont_ntt_{d}" for c in ("bn128", "bls12_381") for d in ("forward", "inverse")]
 G2_SYMBOLS = [f"{c}_G2_proj_MSM_{f}_coeff_{o}_out" for c in ("bn128", "bls12_381") for f in ("std", "mont") for o in ("proj", "affine")]
-GFFT_SYMBOLS = [f"{c}_G1_proj_fft_{d}" for c in ("bn128", "bls12_381") for d in ("forward", "inverse")]
+GFFT_SYMBOLS = [f"{c}_{g}_fft_{d}" for c in ("bn128", "bls12_381") for g in ("G1_proj", "G1_jac", "G2_proj") for d in ("forward", "inverse")]
+EXTRA_SYMBOLS = ([f"{c}_G2_proj_batch_{d}_affine" for c in ("bn128", "bls12_381") for d in ("to", "from")] +
+                 [f"{c}_{g}_out_slow_reference" for c in ("bn128", "bls12_381")
+                  for g in ("G1_proj_MSM_std_coeff_proj", "G1_jac_MSM_std_coeff_jac", "G2_proj_MSM_std_coeff_proj")])
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
                      "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt", "zkb200_device_upload", "zkb200_device_free"]
 
@@ -94,11 +97,11 @@ def lib() -> ctypes.CDLL:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P]
             f.restype = None
-        for name in CONVERT_SYMBOLS:
+        for name in CONVERT_SYMBOLS + EXTRA_SYMBOLS[:4]:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P]
             f.restype = None
-        for name in REFERENCE_SYMBOLS + G2_SYMBOLS:
+        for name in REFERENCE_SYMBOLS + G2_SYMBOLS + EXTRA_SYMBOLS[4:]:
             f = getattr(L, name)
             f.argtypes = [ctypes.c_int, _U64P, _U64P, _U64P, ctypes.c_int] + ([ctypes.c_int] if name.endswith("_variable") else [])
             f.restype = None
@@ -201,14 +204,14 @@ def ntt_device(curve: str, m: int, gen: np.ndarray, src_ptr: int, dst_ptr: int, 
     lib().zkb200_ntt(CURVES[curve]["id"], m, _ptr(g), src_ptr, DEVICE, dst_ptr, DEVICE, int(inverse))
 
 
-def group_fft(curve: str, m: int, gen: np.ndarray, src: np.ndarray, inverse: bool = False) -> np.ndarray:
-    """FFT of 2^m projective G1 points ((N, 3L) uint64) -> normalised projective points, the reference's
-    <curve>_G1_proj_fft_forward / _inverse."""
+def group_fft(curve: str, m: int, gen: np.ndarray, src: np.ndarray, inverse: bool = False, group: str = "G1_proj") -> np.ndarray:
+    """FFT of 2^m group elements ((N, 3 coordinates) uint64) -> normalised points, the reference's
+    <curve>_{G1_proj,G1_jac,G2_proj}_fft_forward / _inverse."""
     a = _as_u64(src)
     assert a.shape[0] == 1 << m
     g = _as_u64(gen).ravel()
     out = np.zeros_like(a)
-    getattr(lib(), f"{curve}_G1_proj_fft_{'inverse' if inverse else 'forward'}")(m, _ptr(g), _ptr(a.ravel()), _ptr(out.ravel()))
+    getattr(lib(), f"{curve}_{group}_fft_{'inverse' if inverse else 'forward'}")(m, _ptr(g), _ptr(a.ravel()), _ptr(out.ravel()))
     return out
 
 

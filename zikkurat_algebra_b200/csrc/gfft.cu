@@ -1,9 +1,10 @@
-// FFT of G1 group elements -- scope row 8f.4 (KZG setup: examples/KZG.hs:55, lib/src/.../G1/Affine.hs:152-157).
+// FFT of group elements (G1 in projective or Jacobian input form, G2 projective) -- scope row 8f.4 (KZG setup: examples/KZG.hs:55, lib/src/.../G1/Affine.hs:152-157).
 // Same semantics as the reference's recursive routines
 //   <curve>_G1_proj_fft_forward / _inverse      lib/cbits/curves/g1/proj/bn128_G1_proj.c:678-789
 //   forward:  tgt[k] = sum_j gen^(j*k) * src[j]            inverse:  tgt[j] = N^-1 * sum_k gen^(-j*k) * src[k]
 // on N = 2^m projective points, natural order in and out, results NORMALISED ((x, y, 1) or the infinity (0, 1, 0)
-// exactly like bn128_G1_proj_normalize, :75-96), hence bit-comparable.
+// exactly like bn128_G1_proj_normalize, :75-96; the Jacobian and G2 twins normalise the same way:
+// bn128_G1_jac.c:62-85, bn128_G2_proj.c:70-89), hence bit-comparable.
 //
 // Radix-2 decimation in time on XYZZ points held in global memory: one launch per stage, one thread per butterfly
 // (a, b) -> (a + w*b, a - w*b); w*b is a 4-bit fixed-window scalar multiplication (the reference does the same per
@@ -47,7 +48,7 @@ __device__ __forceinline__ size_t gfft_bitrev(size_t x, int bits) {
 
 // projective (X:Y:Z) records -> XYZZ, written to the bit-reversed position
 template <class C>
-__global__ void __launch_bounds__(128) k_gfft_load(const uint32_t* __restrict__ src, int m, XyzzMem<typename C::Fp>* __restrict__ dst) {
+__global__ void __launch_bounds__(128) k_gfft_load(const uint32_t* __restrict__ src, int m, int jac, XyzzMem<typename C::Fp>* __restrict__ dst) {
   using P = typename C::Fp;
   constexpr int L = P::L;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(128) k_gfft_load(const uint32_t* __restrict__ 
   const uint32_t* s = src + i * 3 * L;
   Fe<P> X, Y, Z;
   for (int k = 0; k < L; k++) { X.l[k] = s[k]; Y.l[k] = s[L + k]; Z.l[k] = s[2 * L + k]; }
-  store_xyzz<P>(dst + gfft_bitrev(i, m), xyzz_from_proj<P>(X, Y, Z));
+  store_xyzz<P>(dst + gfft_bitrev(i, m), jac ? xyzz_from_jac<P>(X, Y, Z) : xyzz_from_proj<P>(X, Y, Z));
 }
 
 // stage s (1-based): butterflies at distance 2^(s-1) inside blocks of 2^s
@@ -116,18 +117,20 @@ k_gfft_store(const XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* _
 
 template <class C>
 void gfft_device(cudaStream_t s, int m, const uint32_t* d_gen, const uint32_t* d_src, void* d_work, uint32_t* d_table,
-                 uint32_t* d_dst, int inverse) {
+                 uint32_t* d_dst, int inverse, int jac) {
   using Mem = XyzzMem<typename C::Fp>;
   const size_t N = (size_t)1 << m;
   Mem* data = (Mem*)d_work;
   ntt_build_table<typename C::Fr>(s, d_gen, N >> 1, m, d_table);
-  k_gfft_load<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(d_src, m, data);
+  k_gfft_load<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(d_src, m, jac, data);
   for (int st = 1; st <= m; st++)
     k_gfft_stage<C><<<(unsigned)(((N >> 1) + 127) / 128), 128, 0, s>>>(data, d_table, m, st, inverse);
   k_gfft_store<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(data, d_table, m, inverse, d_dst);
 }
 
-template void gfft_device<Bn254>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int);
-template void gfft_device<Bls12381>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int);
+template void gfft_device<Bn254>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
+template void gfft_device<Bls12381>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
+template void gfft_device<Bn254G2>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
+template void gfft_device<Bls12381G2>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
 
 }  // namespace zk

@@ -698,7 +698,7 @@ void run_ntt(int m, const uint64_t* gen, const uint64_t* src, int src_loc, uint6
 
 // FFT of G1 group elements (scope row 8f.4): host buffers in, host buffers out
 template <class C>
-void run_gfft(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, int inverse) {
+void run_gfft(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, int inverse, int jac) {
   constexpr int L = C::Fp::L;
   if (m < 0 || m > 26) { fprintf(stderr, "[zkmsm_b200] fatal: group FFT size 2^%d unsupported\n", m); abort(); }
   DeviceCtx& cx = get_ctx();
@@ -714,7 +714,7 @@ void run_gfft(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, in
   CK(cudaMemcpyAsync(d_gen, gen, 32, cudaMemcpyHostToDevice, s));
   host_to_device(cx, d_src, src, bytes, s);
   g_launches += 3 + m;
-  gfft_device<C>(s, m, d_gen, d_src, d_work, d_table, d_dst, inverse);
+  gfft_device<C>(s, m, d_gen, d_src, d_work, d_table, d_dst, inverse, jac);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -866,14 +866,24 @@ const char* zkb200_version(void) { return "zkmsm_b200 0.1 (sm_100a)"; }
   void NAME##_poly_mont_ntt_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                 \
     run_ntt<CURVE::Fr>(m, gen, src, ZKB200_HOST, tgt, ZKB200_HOST, 1); }
 
-#define ZK_GFFT_SYMBOLS(NAME, CURVE)                                                                                  \
+#define ZK_GFFT_SYMBOLS(NAME, CURVE, CURVE2)                                                                          \
   void NAME##_G1_proj_fft_forward(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                   \
-    run_gfft<CURVE>(m, gen, src, tgt, 0); }                                                                           \
+    run_gfft<CURVE>(m, gen, src, tgt, 0, 0); }                                                                        \
   void NAME##_G1_proj_fft_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                   \
-    run_gfft<CURVE>(m, gen, src, tgt, 1); }
+    run_gfft<CURVE>(m, gen, src, tgt, 1, 0); }                                                                        \
+  void NAME##_G1_jac_fft_forward(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                    \
+    run_gfft<CURVE>(m, gen, src, tgt, 0, 1); }                                                                        \
+  void NAME##_G1_jac_fft_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                    \
+    run_gfft<CURVE>(m, gen, src, tgt, 1, 1); }                                                                        \
+  void NAME##_G2_proj_fft_forward(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                   \
+    run_gfft<CURVE2>(m, gen, src, tgt, 0, 0); }                                                                       \
+  void NAME##_G2_proj_fft_inverse(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt) {                   \
+    run_gfft<CURVE2>(m, gen, src, tgt, 1, 0); }                                                                       \
+  void NAME##_G2_proj_batch_to_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE2>(N, src, tgt, 0, 1); }   \
+  void NAME##_G2_proj_batch_from_affine(int N, const uint64_t* src, uint64_t* tgt) { run_convert<CURVE2>(N, src, tgt, 0, 0); }
 
-ZK_GFFT_SYMBOLS(bn128, Bn254)
-ZK_GFFT_SYMBOLS(bls12_381, Bls12381)
+ZK_GFFT_SYMBOLS(bn128, Bn254, Bn254G2)
+ZK_GFFT_SYMBOLS(bls12_381, Bls12381, Bls12381G2)
 
 ZK_NTT_SYMBOLS(bn128, Bn254)
 ZK_NTT_SYMBOLS(bls12_381, Bls12381)
@@ -891,6 +901,19 @@ ZK_CONVERT_SYMBOLS(bls12_381, Bls12381)
     msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_AFFINE, 0, t); }                                   \
   void NAME##_G2_proj_MSM_mont_coeff_affine_out(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {   \
     msm_entry(ID, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 1, OUT_AFFINE, 0, t); }
+
+// The reference also exports (and never calls) a slow sum-of-scalar-multiplications variant of the std-coefficient MSM
+// (bn128_G1_proj.c:610-619, header name misspelt :47).  Same group element; served by the same pipeline.
+#define ZK_SLOW_REF_SYMBOLS(NAME, ID1, ID2)                                                                                \
+  void NAME##_G1_proj_MSM_std_coeff_proj_out_slow_reference(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) { \
+    msm_entry(ID1, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_PROJ, 0, t); }                                          \
+  void NAME##_G1_jac_MSM_std_coeff_jac_out_slow_reference(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) {   \
+    msm_entry(ID1, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_JAC, 0, t); }                                           \
+  void NAME##_G2_proj_MSM_std_coeff_proj_out_slow_reference(int n, const uint64_t* e, const uint64_t* g, uint64_t* t, int nl) { \
+    msm_entry(ID2, 1, n, e, ZKB200_HOST, g, ZKB200_HOST, nl, 0, OUT_PROJ, 0, t); }
+
+ZK_SLOW_REF_SYMBOLS(bn128, ZKB200_BN128, ZKB200_BN128_G2)
+ZK_SLOW_REF_SYMBOLS(bls12_381, ZKB200_BLS12_381, ZKB200_BLS12_381_G2)
 
 ZK_REF_SYMBOLS_G2(bn128, ZKB200_BN128_G2)
 ZK_REF_SYMBOLS_G2(bls12_381, ZKB200_BLS12_381_G2)
