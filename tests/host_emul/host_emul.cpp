@@ -7,6 +7,8 @@
 #include "curve_params.cuh"
 #include "ec.cuh"
 #include "recode.cuh"
+#include "aff_plan.cuh"
+#include <vector>
 
 using namespace zk;
 
@@ -58,6 +60,8 @@ static Xyzz<P> sum_list(long n, const uint64_t* pts, const uint8_t* neg) {
     st<C::Fp>(t, fe_sub<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b))); }                                                  \
   extern "C" void he_##NAME##_fp_neg(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_neg<C::Fp>(ld<C::Fp>(a))); } \
   extern "C" void he_##NAME##_fp_inv(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_inv<C::Fp>(ld<C::Fp>(a))); } \
+  extern "C" void he_##NAME##_fp_inv_euclid(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_inv_euclid<C::Fp>(ld<C::Fp>(a))); } \
+  extern "C" void he_##NAME##_fr_inv(const uint64_t* a, uint64_t* t) { st<C::Fr>(t, fe_inv<C::Fr>(ld<C::Fr>(a))); } \
   extern "C" void he_##NAME##_fp_inv_fermat(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_inv_fermat<C::Fp>(ld<C::Fp>(a))); } \
   extern "C" void he_##NAME##_fr_sqr(const uint64_t* a, uint64_t* t) { st<C::Fr>(t, fe_sqr<C::Fr>(ld<C::Fr>(a))); }       \
   extern "C" void he_##NAME##_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* t) {                       \
@@ -82,6 +86,86 @@ static Xyzz<P> sum_list(long n, const uint64_t* pts, const uint8_t* neg) {
   }                                                                                                             \
   extern "C" void he_##NAME##_dbl_list(long n, const uint64_t* pts, uint64_t* t_aff) {                          \
     staff<C::Fp>(t_aff, xyzz_dbl<C::Fp>(sum_list<C::Fp>(n, pts, 0))); }
+
+// ---- the affine pre-reduction tree (aff_plan.cuh), walked exactly like kernels_aff.cuh does, one segment --------
+// keys/vals: n sorted pairs (key 0 first); R levels; then the surviving records are added to their buckets the way
+// k_accumulate + fix-up would.  Returns 0, or a negative code when a structural invariant is broken:
+//   -1 a bucket was written twice by the tree, -2 a record touches a bucket the tree has written,
+//   -3 the records are not sorted by key.
+template <class P>
+static int aff_tree_emul(long n, const uint32_t* keys, const uint32_t* vals, const uint64_t* pts, int R, uint32_t NB,
+                         uint64_t* out_affine) {
+  struct St { uint32_t hk, hr, tk, tr; };
+  std::vector<Affine<P>> tmp;
+  std::vector<char> tmp_inf;
+  std::vector<Xyzz<P>> bucket(NB, xyzz_inf<P>());
+  std::vector<char> written(NB, 0);
+  int err = 0;
+  auto load = [&](uint32_t ref, bool& inf) {
+    Affine<P> p;
+    if (ref & AFF_TEMP) { p = tmp[ref & AFF_IDX]; inf = tmp_inf[ref & AFF_IDX]; }
+    else { p = ldaff<P>(pts + (size_t)(ref & AFF_IDX) * P::L); inf = affine_is_inf<P>(p); }
+    if ((ref >> 31) && !inf) p.y = fe_neg<P>(p.y);
+    return p;
+  };
+  auto to_bucket = [&](uint32_t key, const Affine<P>& p, bool inf) {
+    if (written[key - 1]) err = -1;
+    written[key - 1] = 1;
+    bucket[key - 1] = inf ? xyzz_inf<P>() : xyzz_from_affine<P>(p);
+  };
+  std::vector<St> cur(n), nxt;
+  for (long i = 0; i < n; i++) cur[i] = St{keys[i], vals[i], keys[i], vals[i]};
+  for (int r = 0; r < R; r++) {
+    size_t nin = cur.size(), nm = (nin + 1) / 2;
+    nxt.assign(nm, St{0, 0, 0, 0});
+    for (size_t i = 0; i < nm; i++) {
+      St l = cur[2 * i], rr = 2 * i + 1 < nin ? cur[2 * i + 1] : St{0, 0, 0, 0};
+      AffPlan pl = aff_plan(l.hk, l.hr, l.tk, l.tr, rr.hk, rr.hr, rr.tk, rr.tr);
+      if (pl.add) {
+        bool i1, i2;
+        Affine<P> p1 = load(l.tr, i1), p2 = load(rr.hr, i2), sum = p1;
+        Fe<P> d;
+        int cls = aff_classify<P>(p1, i1, p2, i2, d);
+        bool sinf = false;
+        if (cls >= AFF_ADD) sum = aff_finish<P, false>(cls, p1, p2, fe_inv<P>(d));
+        else if (cls == AFF_COPY2) sum = p2;
+        else if (cls == AFF_INF) sinf = true;
+        if (pl.sum_key) to_bucket(pl.sum_key, sum, sinf);
+        uint32_t sref = AFF_TEMP | (uint32_t)tmp.size();
+        tmp.push_back(sum);
+        tmp_inf.push_back(sinf);
+        if (pl.hr == AFF_SUM) pl.hr = sref;
+        if (pl.tr == AFF_SUM) pl.tr = sref;
+      } else {
+        for (int k = 0; k < 2; k++)
+          if (pl.st_key[k]) { bool inf; Affine<P> p = load(pl.st_ref[k], inf); to_bucket(pl.st_key[k], p, inf); }
+      }
+      nxt[i] = St{pl.hk, pl.hr, pl.tk, pl.tr};
+    }
+    cur.swap(nxt);
+  }
+  uint32_t last_key = 0;
+  for (const St& b : cur) {
+    uint32_t rk[2] = {b.hk == b.tk ? 0u : b.hk, b.tk}, rf[2] = {b.hr, b.tr};
+    for (int k = 0; k < 2; k++) {
+      if (!rk[k]) continue;
+      if (rk[k] < last_key) err = -3;
+      last_key = rk[k];
+      if (written[rk[k] - 1]) err = -2;
+      bool inf;
+      Affine<P> p = load(rf[k], inf);
+      if (!inf) xyzz_madd<P>(bucket[rk[k] - 1], p);
+    }
+  }
+  for (uint32_t b = 0; b < NB; b++) staff<P>(out_affine + (size_t)b * P::L, bucket[b]);
+  return err;
+}
+#define DEFINE_AFF(NAME, C)                                                                                        \
+  extern "C" int he_##NAME##_aff_tree(long n, const uint32_t* keys, const uint32_t* vals, const uint64_t* pts, int R, \
+                                      uint32_t NB, uint64_t* out_affine) {                                         \
+    return aff_tree_emul<C::Fp>(n, keys, vals, pts, R, NB, out_affine); }
+DEFINE_AFF(bn128, Bn254)
+DEFINE_AFF(bls12_381, Bls12381)
 
 DEFINE(bn128, Bn254)
 DEFINE(bls12_381, Bls12381)

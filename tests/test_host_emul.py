@@ -21,7 +21,7 @@ CURVES = ["bn128", "bls12_381"]
 
 @pytest.fixture(scope="module")
 def he():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("hd.cuh", "fp.cuh", "ec.cuh", "recode.cuh", "curve_params.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("hd.cuh", "fp.cuh", "ec.cuh", "recode.cuh", "curve_params.cuh", "aff_plan.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", f"-I{CSRC}", SRC, "-o", SO], check=True)
     return ctypes.CDLL(SO)
@@ -51,6 +51,13 @@ def test_fp_ops(he, curve):
         A = _arr(cv.fp_to_bytes(a))
         assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv", A, L).tobytes()) == pow(a, -1, cv.p)
         assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv_fermat", A, L).tobytes()) == pow(a, -1, cv.p)
+        assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv_euclid", A, L).tobytes()) == pow(a, -1, cv.p)
+    # the same inversion over Fr (NTT scaling, batch inversion users): raw residues, R = 2^256
+    Rr = 1 << 256
+    for a in [1, 2, 3, cv.r - 1, cv.r - 2, (cv.r + 1) // 2, 1 << 200] + [rng.randrange(1, cv.r) for _ in range(300)]:
+        A = _arr(a.to_bytes(32, "little"))
+        got = int.from_bytes(refs.call2(he, f"he_{curve}_fr_inv", A, 4).tobytes(), "little")
+        assert got == pow(a, -1, cv.r) * Rr * Rr % cv.r     # (aR')^-1 R'^2 with a = a' R'
 
 
 @pytest.mark.parametrize("curve", CURVES)
@@ -213,3 +220,57 @@ def test_signed_digit_recoding(he):
                     assert 0 <= keys[w] <= (1 << (c - 1))
                     tot += (-keys[w] if negs[w] else keys[w]) << (c * w)
                 assert tot == k, (nbits, c, k)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_affine_tree_bookkeeping_and_arithmetic(he, curve):
+    """The pairwise affine pre-reduction (aff_plan.cuh / kernels_aff.cuh) walked on the host: for every key
+    distribution the tree's direct bucket writes plus the surviving records must add up to the plain per-key
+    sums, with no bucket owned twice.  Includes repeated points (doublings), P/-P pairs, infinity inputs,
+    zero digits and segment lengths that are not powers of two."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    f = getattr(he, f"he_{curve}_aff_tree")
+    U32P = ctypes.POINTER(ctypes.c_uint32)
+    f.argtypes = [ctypes.c_long, U32P, U32P, refs.U64P, ctypes.c_int, ctypes.c_uint32, refs.U64P]
+    f.restype = ctypes.c_int
+    rng = random.Random(11)
+    base = pyec.chain_points(cv, 24, 3, 5)
+    pool = base + [None, base[0], base[0], base[1]]          # infinity and repeated points
+    pts_arr = _arr(cv.points_to_bytes(pool))
+    NB = 8
+    shapes = [
+        lambda n: [rng.randrange(0, NB + 1) for _ in range(n)],          # uniform, with zero digits
+        lambda n: [1 + (i * NB) // n for i in range(n)],                  # equal runs
+        lambda n: [3] * n,                                                # one long run
+        lambda n: [0] * n,                                                # nothing to insert
+        lambda n: [rng.choice([2, 2, 2, 2, 5, 7]) for _ in range(n)],     # skewed
+        lambda n: [min(NB, 1 + i) for i in range(n)],                     # all distinct, then one run
+    ]
+    for n in (1, 2, 3, 5, 8, 13, 32, 45, 64):
+        for shape in shapes:
+            keys = sorted(shape(n))
+            idx = [rng.randrange(len(pool)) for _ in range(n)]
+            neg = [rng.randrange(2) for _ in range(n)]
+            if n >= 8:   # force P + P, P + (-P) and P + inf next to each other inside one run
+                k = keys[n // 2]
+                for j in range(n // 2 - 2, n // 2 + 2):
+                    keys[j] = k
+                keys.sort()
+                j = keys.index(k)
+                idx[j], idx[j + 1], neg[j], neg[j + 1] = 0, 0, 0, 0
+                idx[j + 2], idx[j + 3], neg[j + 2], neg[j + 3] = 1, 1, 0, 1
+            want = [None] * NB
+            for kk, i, s in zip(keys, idx, neg):
+                if kk:
+                    p = pool[i]
+                    want[kk - 1] = cv.add(want[kk - 1], cv.neg(p) if s else p)
+            ka = np.array(keys, np.uint32)
+            va = np.array([i | (s << 31) for i, s in zip(idx, neg)], np.uint32)
+            for R in (0, 1, 2, 3, 4, 7):
+                out = np.zeros(NB * 2 * L, np.uint64)
+                rc = f(n, ka.ctypes.data_as(U32P), va.ctypes.data_as(U32P), refs.ptr(pts_arr), R, NB, refs.ptr(out))
+                assert rc == 0, (n, keys, R, rc)
+                got = out.tobytes()
+                for b in range(NB):
+                    assert got[b * 16 * L:(b + 1) * 16 * L] == cv.affine_to_bytes(want[b]), (n, keys, R, b)

@@ -660,3 +660,90 @@ def test_remaining_twins_of_the_next_rows(zk, curve):
     got = zk.call_reference_symbol(sym, sc, g2pts)
     assert (refs.call2(lib, f"{curve}_G2_proj_to_affine", got, W).tobytes()
             == refs.call2(lib, f"{curve}_G2_proj_to_affine", ref_out, W).tobytes())
+
+
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_affine_pre_reduction_levels(zk, curve):
+    """$ZKB200_AFFINE = R: R levels of pairwise batched-affine sums in front of the XYZZ accumulation
+    (kernels_aff.cuh).  Every R must give the reference's bytes: ragged n, narrow windows (long runs), wide
+    windows (no runs at all), repeated points, P/-P pairs, infinity inputs, both scalar forms, input slices."""
+    cv = pyec.CURVES[curve]
+    pts_all = refs.chain_points(curve, 6001)
+    for n in (2, 3, 5, 64, 257, 1000, 6001):
+        pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=100 + n, reduce=False)
+        want = cpu_affine(curve, sc, pts).tobytes()
+        for R in (1, 2, 3, 5, 9):
+            with _Env(ZKB200_AFFINE=R):
+                got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
+            assert got.tobytes() == want, (n, R)
+    # window widths: c = 2 gives runs of ~n/2, c = 16 gives almost no equal keys
+    n = 3000
+    pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=7, reduce=False)
+    want = cpu_affine(curve, sc, pts).tobytes()
+    for c in (1, 2, 5, 9, 16):
+        for R in (1, 4):
+            with _Env(ZKB200_AFFINE=R):
+                out = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_proj_out_variable", sc, pts, window_size=c)
+            assert to_affine_cpu(curve, "proj", out).tobytes() == want, (c, R)
+    # exceptional shapes inside the batched additions
+    G = cv.gen
+    P, Q = cv.mul(7, G), cv.mul(1234567, G)
+    sets = {
+        "repeated": ([3] * 9, [P] * 9),
+        "repeated_mixed": ([3, 3, 3, 8, 8, 8, 8], [P, P, Q, Q, Q, P, P]),
+        "neg_pairs": ([77] * 8, [P, Q, cv.neg(P), cv.neg(Q), P, cv.neg(P), Q, Q]),
+        "inf_inputs": ([9, 9, 9, 9, 2, 2], [None, P, None, None, Q, None]),
+        "same_scalar_many_points": ([0xABCDEF] * 200, pyec.chain_points(cv, 200, 9, 11)),
+        "all_cancel": ([5] * 4, [P, cv.neg(P), Q, cv.neg(Q)]),
+    }
+    for name, (ks, pl) in sets.items():
+        want = cv.affine_to_bytes(cv.msm(ks, pl))
+        Pb = np.frombuffer(cv.points_to_bytes(pl), dtype=np.uint64).copy()
+        Sm = np.frombuffer(b"".join(cv.scalar_mont_bytes(k) for k in ks), dtype=np.uint64).copy()
+        for R in (1, 2, 3):
+            for c in (0, 3):
+                with _Env(ZKB200_AFFINE=R, ZKB200_WINDOW=c):
+                    got = zk.call_reference_symbol(f"{curve}_G1_jac_MSM_mont_coeff_affine_out", Sm, Pb)
+                assert got.tobytes() == want, (name, R, c)
+    # input slices + batch entry point
+    n = 5003
+    pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=3, reduce=True)
+    want = cpu_affine(curve, sc, pts, "mont").tobytes()
+    for K in (1, 3):
+        with _Env(ZKB200_AFFINE=3, ZKB200_SLICES=K):
+            got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_mont_coeff_affine_out", sc, pts)
+        assert got.tobytes() == want, K
+    nm = 3
+    scb = np.concatenate([refs.random_scalars(curve, 1000, seed=40 + i, reduce=True) for i in range(nm)])
+    with _Env(ZKB200_AFFINE=2):
+        outs = zk.msm_batch(curve, scb.reshape(nm, 1000, 4), pts_all[:1000], mont=True)
+    for i in range(nm):
+        w = cpu_affine(curve, scb.reshape(nm, 1000, 4)[i], pts_all[:1000], "mont").tobytes()
+        assert np.asarray(outs[i]).tobytes() == w, i
+
+
+def test_affine_pre_reduction_mid_size_vs_threaded_reference(zk):
+    curve, n = "bls12_381", 1 << 17
+    pts = refs.chain_points(curve, n)
+    sc = refs.random_scalars(curve, n, seed=23)
+    want = refs.ref_msm_threads(curve, sc, pts, mont=True, nthreads=os.cpu_count() or 4).tobytes()
+    for R in (2, 4):
+        with _Env(ZKB200_AFFINE=R):
+            got = zk.msm(curve, sc, pts, mont=True, out="affine")
+        assert got.tobytes() == want, R

@@ -448,7 +448,7 @@ ZK_HD bool big_lt(const uint32_t* a, const uint32_t* b) {  // a < b
   return subc(0u, 0u) != 0u;
 }
 template <class P>
-ZK_HD Fe<P> fe_inv(const Fe<P>& a) {  // a != 0, canonical; returns the Montgomery form of 1/a
+ZK_HD Fe<P> fe_inv_euclid(const Fe<P>& a) {  // a != 0, canonical; returns the Montgomery form of 1/a
   constexpr int L = P::L;
   uint32_t u[L], v[L];
   Fe<P> x1 = fe_zero<P>(), x2 = fe_zero<P>();
@@ -467,6 +467,98 @@ ZK_HD Fe<P> fe_inv(const Fe<P>& a) {  // a != 0, canonical; returns the Montgome
 #pragma unroll
   for (int i = 0; i < L; i++) r3.l[i] = P::r3(i);
   return fe_mul<P>(r, r3);
+}
+
+
+// ---- inversion, fast path: Kaliski's almost-Montgomery inverse ------------------------------------------------
+// Phase 1 is the same binary gcd walk, but the cofactors r, s are only shifted and added -- no modular halving
+// inside the loop -- so an iteration is one subtraction and one addition (independent carry chains) instead of
+// six dependent ones.  It ends with  x = a^-1 * 2^k mod p,  bits <= k <= 2*bits.  Phase 2 removes 2^k and
+// restores the Montgomery scale with three multiplications:
+//   x * R^3/R = x*R^2;   then  * 2^e1 / R  and  * 2^e2 / R  with  e1 + e2 = 2*32L - k   =>   a^-1 * R^2 (a = residue).
+// The result is the canonical inverse, bit-identical to fe_inv_euclid (tests/test_host_emul.py).
+template <int L>
+ZK_HD void big_shl1(uint32_t* a) {
+#pragma unroll
+  for (int i = L - 1; i > 0; i--) a[i] = (a[i] << 1) | (a[i - 1] >> 31);
+  a[0] <<= 1;
+}
+template <int L>
+ZK_HD bool big_is_zero(const uint32_t* a) {
+  uint32_t o = a[0];
+#pragma unroll
+  for (int i = 1; i < L; i++) o |= a[i];
+  return o == 0;
+}
+template <class P>
+ZK_HD Fe<P> fe_pow2(int e) {  // 2^e as a plain integer, e < 32L
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < P::L; i++) r.l[i] = (i == (e >> 5)) ? (1u << (e & 31)) : 0u;
+  return r;
+}
+template <class P>
+ZK_HD Fe<P> fe_inv(const Fe<P>& a) {  // a != 0, canonical; returns the Montgomery form of 1/a
+  constexpr int L = P::L;
+  uint32_t u[L], v[L], r[L], s[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) { u[i] = P::mod(i); v[i] = a.l[i]; r[i] = 0; s[i] = 0; }
+  s[0] = 1;
+  int k = 0;
+  for (; k < 2 * P::BITS + 2; k++) {
+    if (big_is_zero<L>(v)) break;
+    if ((u[0] & 1u) == 0) {
+      big_shr1<L>(u, 0u);
+      big_shl1<L>(s);
+    } else if ((v[0] & 1u) == 0) {
+      big_shr1<L>(v, 0u);
+      big_shl1<L>(r);
+    } else {
+      uint32_t d1[L], d2[L], rs[L];   // u - v, v - u, r + s: three independent carry chains
+      d1[0] = sub_cc(u[0], v[0]);
+#pragma unroll
+      for (int i = 1; i < L; i++) d1[i] = subc_cc(u[i], v[i]);
+      const bool v_ge_u_strict_or_eq = subc(0u, 0u) != 0u;   // borrow: u < v
+      d2[0] = sub_cc(v[0], u[0]);
+#pragma unroll
+      for (int i = 1; i < L; i++) d2[i] = subc_cc(v[i], u[i]);
+      rs[0] = add_cc(r[0], s[0]);
+#pragma unroll
+      for (int i = 1; i < L - 1; i++) rs[i] = addc_cc(r[i], s[i]);
+      rs[L - 1] = addc(r[L - 1], s[L - 1]);
+      const bool u_gt_v = !v_ge_u_strict_or_eq && !big_is_zero<L>(d1);
+      if (u_gt_v) {
+#pragma unroll
+        for (int i = 0; i < L; i++) { u[i] = d1[i]; r[i] = rs[i]; }
+        big_shr1<L>(u, 0u);
+        big_shl1<L>(s);
+      } else {
+#pragma unroll
+        for (int i = 0; i < L; i++) { v[i] = d2[i]; s[i] = rs[i]; }
+        big_shr1<L>(v, 0u);
+        big_shl1<L>(r);
+      }
+    }
+  }
+  // r < 2p:  x = p - (r mod p)
+  uint32_t pm[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) pm[i] = P::mod(i);
+  if (!big_lt<L>(r, pm)) big_sub_borrow<L>(r, pm);
+  Fe<P> x;
+  x.l[0] = sub_cc(pm[0], r[0]);
+#pragma unroll
+  for (int i = 1; i < L - 1; i++) x.l[i] = subc_cc(pm[i], r[i]);
+  x.l[L - 1] = subc(pm[L - 1], r[L - 1]);
+  Fe<P> r3;
+#pragma unroll
+  for (int i = 0; i < L; i++) r3.l[i] = P::r3(i);
+  const int e_total = 2 * 32 * L - k;
+  const int e1 = e_total < P::BITS - 1 ? e_total : P::BITS - 1;
+  const int e2 = e_total - e1;
+  Fe<P> t = fe_mul<P>(x, r3);
+  t = fe_mul<P>(t, fe_pow2<P>(e1));
+  return fe_mul<P>(t, fe_pow2<P>(e2));
 }
 
 }  // namespace zk

@@ -1,0 +1,494 @@
+// Affine pre-reduction of the sorted pairs ("batched affine additions") in front of the XYZZ bucket accumulation.
+//
+// Why: one bucket insertion in XYZZ coordinates costs 8M+2S.  Adding two AFFINE points costs 2M+1S plus one
+// field inversion, and n independent inversions cost one inversion plus 3(n-1) multiplications (Montgomery's
+// trick): 5M+1S per addition when millions of them share the inversion.  The reference has no counterpart
+// (its bucket loop is bn128_G1_proj.c:520-561, one madd_proj_aff per point); the results are the same group
+// elements, and the library's output is the canonical affine sum either way.
+//
+// How: the sorted pairs of every segment are summed pairwise, level by level (aff_plan.cuh explains the block
+// bookkeeping that makes this exact for any key distribution).  One level = three steps on the stream:
+//   k_aff_prod    every thread walks AFF_B merges, forms the denominators d = x2 - x1 (2y for a doubling) and
+//                 stores their running product in front of each merge; thread totals go to E[0]
+//   batch_invert  inverts all thread totals: a few tiny kernels (warp-scan product trees, one fe_inv at the top)
+//   k_aff_add     walks the same merges backwards, peels 1/d off the inverted total, finishes the additions,
+//                 writes the sums to the temporary point array and the merged block states for the next level
+// After R levels the 2 * ceil(n / 2^R) surviving (key, ref) records per segment go through the ordinary
+// k_accumulate / fix-up path; runs that were closed inside a block were already written to their buckets.
+// P+P, P+(-P) and infinity operands are classified per merge and keep their exact group-law meaning.
+#pragma once
+#include "aff_plan.cuh"
+#include "kernels_acc.cuh"
+#include "msm_common.cuh"
+
+namespace zk {
+
+#if defined(__CUDACC__)
+
+template <class P>
+ZK_D Fe<P> ld_fe(const uint32_t* p) {
+  Fe<P> r;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < P::L / 4; k++) {
+    uint4 v = q[k];
+    r.l[4 * k] = v.x; r.l[4 * k + 1] = v.y; r.l[4 * k + 2] = v.z; r.l[4 * k + 3] = v.w;
+  }
+  return r;
+}
+template <class P>
+ZK_D void st_fe(uint32_t* p, const Fe<P>& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < P::L / 4; k++) q[k] = make_uint4(v.l[4 * k], v.l[4 * k + 1], v.l[4 * k + 2], v.l[4 * k + 3]);
+}
+
+template <class P>
+ZK_D const uint32_t* aff_addr(const uint32_t* points, const uint32_t* tmp, uint32_t ref) {
+  return ((ref & AFF_TEMP) ? tmp : points) + (size_t)(ref & AFF_IDX) * (2 * P::L);
+}
+// the point a ref names, sign applied; inf = it is the point at infinity
+template <class P>
+ZK_D Affine<P> aff_load(const uint32_t* points, const uint32_t* tmp, uint32_t ref, bool& inf) {
+  const uint32_t* a = aff_addr<P>(points, tmp, ref);
+  Affine<P> p;
+  p.x = ld_fe<P>(a);
+  p.y = ld_fe<P>(a + P::L);
+  inf = affine_is_inf<P>(p);
+  if ((ref >> 31) && !inf) p.y = fe_neg<P>(p.y);
+  return p;
+}
+template <class P>
+ZK_D void aff_store(uint32_t* tmp, size_t slot, const Affine<P>& p, bool inf) {
+  uint32_t* a = tmp + slot * (2 * P::L);
+  if (inf) {
+    uint4* q = reinterpret_cast<uint4*>(a);
+#pragma unroll
+    for (int k = 0; k < P::L / 2; k++) q[k] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  } else {
+    st_fe<P>(a, p.x);
+    st_fe<P>(a + P::L, p.y);
+  }
+}
+template <class P>
+ZK_D void aff_to_bucket(XyzzMem<P>* b, const Affine<P>& p, bool inf) {
+  store_xyzz<P>(b, inf ? xyzz_inf<P>() : xyzz_from_affine<P>(p));
+}
+
+// The two blocks of merge i of a segment.  LEVEL0: blocks are the sorted pairs themselves.
+struct AffPair {
+  uint32_t Lhk, Lhr, Ltk, Ltr, Rhk, Rhr, Rtk, Rtr;
+};
+template <bool LEVEL0>
+ZK_D AffPair aff_read_pair(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in,
+                           uint32_t nin, uint32_t seg, uint32_t i) {
+  AffPair a;
+  const size_t base = (size_t)seg * nin + 2 * (size_t)i;
+  const bool hasR = 2 * i + 1 < nin;
+  if (LEVEL0) {
+    a.Lhk = a.Ltk = keys[base];
+    a.Lhr = a.Ltr = vals[base];
+    a.Rhk = a.Rtk = hasR ? keys[base + 1] : 0u;
+    a.Rhr = a.Rtr = hasR ? vals[base + 1] : 0u;
+  } else {
+    uint4 l = st_in[base];
+    uint4 r = hasR ? st_in[base + 1] : make_uint4(0u, 0u, 0u, 0u);
+    a.Lhk = l.x; a.Lhr = l.y; a.Ltk = l.z; a.Ltr = l.w;
+    a.Rhk = r.x; a.Rhr = r.y; a.Rtk = r.z; a.Rtr = r.w;
+  }
+  return a;
+}
+
+// ---- step 1: denominators and their running products ------------------------------------------------------
+// nin = blocks per segment on this level, nm = ceil(nin/2) merges per segment, total = nseg * nm.
+// pre[m] = product of the denominators of this thread's earlier merges (written only where merge m adds).
+template <class C, bool LEVEL0>
+__global__ void __launch_bounds__(AFF_THREADS)
+k_aff_prod(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
+           uint32_t nm, uint32_t total, const uint32_t* points, const uint32_t* tmp, uint32_t* __restrict__ pre,
+           uint32_t* __restrict__ tot) {
+  using P = typename C::Fp;
+  constexpr bool CALLS = (P::L > 8);
+  const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * AFF_B);
+  Fe<P> run = fe_one<P>();
+  for (int j = 0; j < AFF_B; j++) {
+    const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
+    if (m >= total) break;
+    const uint32_t seg = m / nm, i = m - seg * nm;
+    AffPair a = aff_read_pair<LEVEL0>(keys, vals, st_in, nin, seg, i);
+    if (!(a.Ltk == a.Rhk && a.Ltk != 0)) continue;
+    // x coordinates decide almost always; the full points are fetched only for the exceptional shapes
+    const uint32_t* a1 = aff_addr<P>(points, tmp, a.Ltr);
+    const uint32_t* a2 = aff_addr<P>(points, tmp, a.Rhr);
+    Fe<P> x1 = ld_fe<P>(a1), x2 = ld_fe<P>(a2), d;
+    int cls;
+    if (x1.l[P::L - 1] == 0xffffffffu || x2.l[P::L - 1] == 0xffffffffu || fe_eq<P>(x1, x2)) {
+      bool i1, i2;
+      Affine<P> p1 = aff_load<P>(points, tmp, a.Ltr, i1), p2 = aff_load<P>(points, tmp, a.Rhr, i2);
+      cls = aff_classify<P>(p1, i1, p2, i2, d);
+    } else {
+      d = fe_sub<P>(x2, x1);
+      cls = AFF_ADD;
+    }
+    if (cls < AFF_ADD) continue;
+    st_fe<P>(pre + (size_t)m * P::L, run);
+    run = aff_mul<P, CALLS>(run, d);
+  }
+  st_fe<P>(tot + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L, run);
+}
+
+// ---- step 3: finish the additions, write sums and merged states ---------------------------------------------
+// totinv[t] = inverse of thread t's total.  Sums go to tmp[tmp_off + m].  Output: st_out[m] (uint4 states) or,
+// on the LAST level, split (key, ref) records for k_accumulate: 2 per block, head slot 0 when the block is one run.
+template <class C, bool LEVEL0, bool LAST>
+__global__ void __launch_bounds__(AFF_THREADS)
+k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
+          uint32_t nm, uint32_t total, const uint32_t* points, uint32_t* tmp, uint32_t tmp_off, const uint32_t* __restrict__ pre,
+          const uint32_t* __restrict__ totinv, uint4* __restrict__ st_out, uint32_t* __restrict__ keys_out,
+          uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets) {
+  using P = typename C::Fp;
+  constexpr bool CALLS = (P::L > 8);
+  const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * AFF_B);
+  Fe<P> r = ld_fe<P>(totinv + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L);
+  for (int j = AFF_B - 1; j >= 0; j--) {
+    const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
+    if (m >= total) continue;
+    const uint32_t seg = m / nm, i = m - seg * nm;
+    AffPair a = aff_read_pair<LEVEL0>(keys, vals, st_in, nin, seg, i);
+    AffPlan pl = aff_plan(a.Lhk, a.Lhr, a.Ltk, a.Ltr, a.Rhk, a.Rhr, a.Rtk, a.Rtr);
+    XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
+    if (pl.add) {
+      bool i1, i2;
+      Affine<P> p1 = aff_load<P>(points, tmp, a.Ltr, i1), p2 = aff_load<P>(points, tmp, a.Rhr, i2);
+      Fe<P> d;
+      const int cls = aff_classify<P>(p1, i1, p2, i2, d);
+      Affine<P> s = p1;
+      bool sinf = false;
+      if (cls >= AFF_ADD) {
+        Fe<P> dinv = aff_mul<P, CALLS>(r, ld_fe<P>(pre + (size_t)m * P::L));
+        r = aff_mul<P, CALLS>(r, d);
+        s = aff_finish<P, CALLS>(cls, p1, p2, dinv);
+      } else if (cls == AFF_COPY2) {
+        s = p2;
+      } else if (cls == AFF_INF) {
+        sinf = true;
+      }
+      if (pl.sum_key != 0) aff_to_bucket<P>(bseg + (pl.sum_key - 1), s, sinf);
+      else aff_store<P>(tmp, (size_t)tmp_off + m, s, sinf);
+      const uint32_t sref = AFF_TEMP | (tmp_off + m);
+      if (pl.hr == AFF_SUM) pl.hr = sref;
+      if (pl.tr == AFF_SUM) pl.tr = sref;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (pl.st_key[k] != 0) {
+          bool inf;
+          Affine<P> p = aff_load<P>(points, tmp, pl.st_ref[k], inf);
+          aff_to_bucket<P>(bseg + (pl.st_key[k] - 1), p, inf);
+        }
+      }
+    }
+    if (LAST) {
+      const size_t o = ((size_t)seg * nm + i) * 2;
+      keys_out[o] = pl.hk == pl.tk ? 0u : pl.hk;
+      vals_out[o] = pl.hk == pl.tk ? 0u : pl.hr;
+      keys_out[o + 1] = pl.tk;
+      vals_out[o + 1] = pl.tk == 0 ? 0u : pl.tr;
+    } else {
+      st_out[m] = make_uint4(pl.hk, pl.hr, pl.tk, pl.tr);
+    }
+  }
+}
+
+// ---- step 2: batch inversion of an array of field elements ------------------------------------------------
+// One tree level: every thread multiplies BINV_G consecutive elements (exclusive prefixes to PRE), the warp
+// multiplies its 32 thread totals with two shuffle scans; X[t] = product of the OTHER lanes' totals, so that
+// 1/total_t = X[t] / warp_total.  Warp totals form the next level's elements.
+template <class P>
+ZK_D Fe<P> shfl_fe(const Fe<P>& v, int delta, bool up) {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < P::L; i++) r.l[i] = up ? __shfl_up_sync(0xffffffffu, v.l[i], delta) : __shfl_down_sync(0xffffffffu, v.l[i], delta);
+  return r;
+}
+template <class P>
+ZK_D void binv_warp_products(const Fe<P>& mine, Fe<P>& others, Fe<P>& all) {
+  constexpr bool CALLS = (P::L > 8);
+  const int lane = threadIdx.x & 31;
+  Fe<P> s = mine;                                   // inclusive prefix product over lanes
+#pragma unroll 1
+  for (int off = 1; off < 32; off <<= 1) {
+    Fe<P> y = shfl_fe<P>(s, off, true);
+    Fe<P> z = aff_mul<P, CALLS>(s, y);
+    if (lane >= off) s = z;
+  }
+  Fe<P> q = mine;                                   // inclusive suffix product
+#pragma unroll 1
+  for (int off = 1; off < 32; off <<= 1) {
+    Fe<P> y = shfl_fe<P>(q, off, false);
+    Fe<P> z = aff_mul<P, CALLS>(q, y);
+    if (lane + off < 32) q = z;
+  }
+  Fe<P> sx = shfl_fe<P>(s, 1, true), qx = shfl_fe<P>(q, 1, false);
+  if (lane == 0) sx = fe_one<P>();
+  if (lane == 31) qx = fe_one<P>();
+  others = aff_mul<P, CALLS>(sx, qx);
+#pragma unroll
+  for (int i = 0; i < P::L; i++) all.l[i] = __shfl_sync(0xffffffffu, s.l[i], 31);
+}
+template <class P, int G = BINV_G>
+ZK_D Fe<P> binv_thread_up(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE, uint32_t t) {
+  constexpr bool CALLS = (P::L > 8);
+  Fe<P> run = fe_one<P>();
+#pragma unroll 1
+  for (int k = 0; k < G; k++) {
+    const size_t idx = (size_t)t * G + k;
+    if (idx < T) {
+      st_fe<P>(PRE + idx * P::L, run);
+      run = aff_mul<P, CALLS>(run, ld_fe<P>(E + idx * P::L));
+    }
+  }
+  return run;
+}
+template <class P, int G = BINV_G>
+ZK_D void binv_thread_down(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE, uint32_t t, Fe<P> r) {
+  constexpr bool CALLS = (P::L > 8);
+#pragma unroll 1
+  for (int k = G - 1; k >= 0; k--) {
+    const size_t idx = (size_t)t * G + k;
+    if (idx < T) {
+      Fe<P> p = ld_fe<P>(PRE + idx * P::L), e = ld_fe<P>(E + idx * P::L);
+      st_fe<P>(PRE + idx * P::L, aff_mul<P, CALLS>(r, p));
+      r = aff_mul<P, CALLS>(r, e);
+    }
+  }
+}
+
+template <class P>
+__global__ void __launch_bounds__(128) k_binv_up(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE,
+                                                 uint32_t* __restrict__ X, uint32_t* __restrict__ Eout) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;     // whole warps: no early exit before the shuffles
+  Fe<P> mine = binv_thread_up<P>(E, T, PRE, t), others, all;
+  binv_warp_products<P>(mine, others, all);
+  if ((size_t)t * BINV_G < T) st_fe<P>(X + (size_t)t * P::L, others);
+  if ((threadIdx.x & 31) == 31 && (size_t)(t & ~31u) * BINV_G < T) st_fe<P>(Eout + (size_t)(t >> 5) * P::L, all);
+}
+template <class P>
+__global__ void __launch_bounds__(128) k_binv_down(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE,
+                                                   const uint32_t* __restrict__ X, const uint32_t* __restrict__ INVup) {
+  constexpr bool CALLS = (P::L > 8);
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((size_t)t * BINV_G >= T) return;
+  Fe<P> r = aff_mul<P, CALLS>(ld_fe<P>(INVup + (size_t)(t >> 5) * P::L), ld_fe<P>(X + (size_t)t * P::L));
+  binv_thread_down<P>(E, T, PRE, t, r);
+}
+// thread-serial level: BINV_GS elements per thread, totals are the next level's elements
+template <class P>
+__global__ void __launch_bounds__(128) k_binv_up_ser(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE,
+                                                     uint32_t* __restrict__ Eout) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((size_t)t * BINV_GS >= T) return;
+  st_fe<P>(Eout + (size_t)t * P::L, binv_thread_up<P, BINV_GS>(E, T, PRE, t));
+}
+template <class P>
+__global__ void __launch_bounds__(128) k_binv_down_ser(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE,
+                                                       const uint32_t* __restrict__ INVup) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((size_t)t * BINV_GS >= T) return;
+  binv_thread_down<P, BINV_GS>(E, T, PRE, t, ld_fe<P>(INVup + (size_t)t * P::L));
+}
+// top of the tree: at most 32 * BINV_G elements, one warp, the only field inversion of the whole batch
+template <class P>
+__global__ void __launch_bounds__(32) k_binv_top(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE) {
+  constexpr bool CALLS = (P::L > 8);
+  const uint32_t t = threadIdx.x;
+  Fe<P> mine = binv_thread_up<P>(E, T, PRE, t), others, all;
+  binv_warp_products<P>(mine, others, all);
+  Fe<P> inv = fe_inv<P>(all);                       // identical data in all lanes: no divergence
+  binv_thread_down<P>(E, T, PRE, t, aff_mul<P, CALLS>(inv, others));
+}
+
+// Workspace layout of batch_invert (binv_workspace_elems in msm_common.cuh): levels l = 0.. with T[l] elements;
+// per level PRE_l (T[l] elements), X_l (ceil(T[l]/G)), E_{l+1} (ceil(T[l]/(32G))).  Result: PRE_0.
+template <class P>
+int batch_invert(cudaStream_t s, const uint32_t* E0, size_t T0, uint32_t* ws, uint32_t** inv_out) {
+  constexpr int L = P::L;
+  BinvLevel lv[16];
+  const int nl = binv_plan(T0, lv);
+  const uint32_t* E[16];
+  uint32_t *PRE[16], *X[16];
+  int launches = 0;
+  E[0] = E0;
+  uint32_t* w = ws;
+  for (int i = 0; i < nl; i++) {
+    const size_t T = lv[i].T;
+    PRE[i] = w; w += T * L;
+    X[i] = w; w += ((T + BINV_G - 1) / BINV_G + 32) * L;
+    if (lv[i].kind == 2) {
+      k_binv_top<P><<<1, 32, 0, s>>>(E[i], (uint32_t)T, PRE[i]);
+      launches++;
+      break;
+    }
+    uint32_t* En = w; w += (lv[i + 1].T + 32) * L;
+    if (lv[i].kind == 0) {
+      size_t threads = (T + BINV_GS - 1) / BINV_GS;
+      k_binv_up_ser<P><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(E[i], (uint32_t)T, PRE[i], En);
+    } else {
+      size_t threads = (((T + BINV_G - 1) / BINV_G) + 31) & ~(size_t)31;
+      k_binv_up<P><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(E[i], (uint32_t)T, PRE[i], X[i], En);
+    }
+    launches++;
+    E[i + 1] = En;
+  }
+  for (int i = nl - 2; i >= 0; i--) {
+    const size_t T = lv[i].T;
+    if (lv[i].kind == 0) {
+      size_t threads = (T + BINV_GS - 1) / BINV_GS;
+      k_binv_down_ser<P><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(E[i], (uint32_t)T, PRE[i], PRE[i + 1]);
+    } else {
+      size_t threads = (T + BINV_G - 1) / BINV_G;
+      k_binv_down<P><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(E[i], (uint32_t)T, PRE[i], X[i], PRE[i + 1]);
+    }
+    launches++;
+  }
+  *inv_out = PRE[0];
+  return launches;
+}
+
+// ---- host driver: R levels over sorted pairs ------------------------------------------------------------------
+template <class C>
+int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int nseg,
+                       int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w) {
+  using P = typename C::Fp;
+  int launches = 0;
+  uint32_t nin = (uint32_t)n, tmp_off = 0;
+  for (int r = 0; r < R; r++) {
+    const uint32_t nm = (nin + 1) / 2;
+    const uint32_t total = (uint32_t)nseg * nm;
+    const unsigned blocks = (total + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
+    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1];
+    uint4* st_out = w.st[r & 1];
+    uint32_t* tot = w.binv;
+    const size_t T0 = (size_t)blocks * AFF_THREADS;
+    if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, s>>>(keys, vals, st_in, nin, nm, total, points, w.tmp, w.pre, tot);
+    else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, s>>>(keys, vals, st_in, nin, nm, total, points, w.tmp, w.pre, tot);
+    uint32_t* inv = nullptr;
+    launches += 1 + batch_invert<P>(s, tot, T0, tot + T0 * P::L, &inv);
+    const bool last = r == R - 1;
+#define ZK_AFF_ADD(L0, LA)                                                                                                  \
+  k_aff_add<C, L0, LA><<<blocks, AFF_THREADS, 0, s>>>(keys, vals, st_in, nin, nm, total, points, w.tmp, tmp_off, w.pre, inv, \
+                                                      st_out, w.keys_out, w.vals_out, NB, buckets)
+    if (r == 0 && last) ZK_AFF_ADD(true, true);
+    else if (r == 0) ZK_AFF_ADD(true, false);
+    else if (last) ZK_AFF_ADD(false, true);
+    else ZK_AFF_ADD(false, false);
+#undef ZK_AFF_ADD
+    launches++;
+    tmp_off += total;
+    nin = nm;
+  }
+  return launches;
+}
+
+// ---- XYZZ accumulation of the surviving records -----------------------------------------------------------------
+// k_accumulate (kernels_acc.cuh) over the record list of the last tree level: `chunk` record SLOTS per thread, empty
+// slots (key 0) skipped per lane so that every trip of the loop adds a real record; a value with bit 30 set names a
+// point of the temporary array.  Same ownership rules: the chunk's first run goes to heads[t] (it may continue the
+// previous chunk's last run), every other run is complete for this level and is stored to its bucket.
+template <class C, bool CALLS, int MINB = (C::Fp::L <= 8 ? 4 : (C::Fp::L <= 12 ? 3 : 2))>
+__global__ void __launch_bounds__(128, MINB)
+k_accumulate_rec(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ points,
+                 const uint32_t* __restrict__ tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
+                 XyzzMem<typename C::Fp>* __restrict__ buckets, XyzzMem<typename C::Fp>* __restrict__ heads,
+                 uint32_t* __restrict__ head_keys) {
+  using P = typename C::Fp;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nseg * chunks_per_seg) return;
+  uint32_t seg = (uint32_t)(t / chunks_per_seg);
+  uint32_t j = (uint32_t)(t - (size_t)seg * chunks_per_seg);
+  size_t start = (size_t)j * chunk;
+  size_t end = start + chunk < n ? start + chunk : n;
+  const uint32_t* kp = keys + (size_t)seg * n;
+  const uint32_t* vp = vals + (size_t)seg * n;
+  XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
+  constexpr int PW = (2 * P::L) / 4;
+  __shared__ uint4 stage[2][PW][128];
+  auto prefetch = [&](int buf, uint32_t v) {
+    const uint4* src = reinterpret_cast<const uint4*>(aff_addr<P>(points, tmp_points, v));
+#pragma unroll
+    for (int w = 0; w < PW; w++) {
+      unsigned dst = (unsigned)__cvta_generic_to_shared(&stage[buf][w][threadIdx.x]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + w) : "memory");
+    }
+  };
+  auto skip = [&](size_t e) { while (e < end && kp[e] == 0) e++; return e; };
+  Xyzz<P> acc = xyzz_inf<P>();
+  uint32_t cur = 0, head_key = 0;
+  bool head_open = true;
+  size_t e0 = skip(start), e1 = end;
+  uint32_t k0 = 0, v0 = 0, k1 = 0, v1 = 0;
+  if (e0 < end) { k0 = kp[e0]; v0 = vp[e0]; prefetch(0, v0); e1 = skip(e0 + 1); }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (e1 < end) { k1 = kp[e1]; v1 = vp[e1]; }
+  int b = 0;
+  while (e0 < end) {
+    size_t e2 = end;
+    uint32_t k2 = 0, v2 = 0;
+    if (e1 < end) { prefetch(b ^ 1, v1); e2 = skip(e1 + 1); }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (e2 < end) { k2 = kp[e2]; v2 = vp[e2]; }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    Affine<P> pt;
+    {
+      uint32_t w32[2 * P::L];
+#pragma unroll
+      for (int w = 0; w < PW; w++) {
+        uint4 q = stage[b][w][threadIdx.x];
+        w32[4 * w] = q.x; w32[4 * w + 1] = q.y; w32[4 * w + 2] = q.z; w32[4 * w + 3] = q.w;
+      }
+#pragma unroll
+      for (int k = 0; k < P::L; k++) { pt.x.l[k] = w32[k]; pt.y.l[k] = w32[P::L + k]; }
+    }
+    const bool inf = affine_is_inf<P>(pt);
+    Fe<P> ny = fe_neg<P>(pt.y);
+    if (v0 >> 31) pt.y = ny;
+    if (k0 != cur) {
+      if (cur != 0) {
+        if (head_open) { store_xyzz<P>(heads + t, acc); head_key = cur; head_open = false; }
+        else store_xyzz<P>(bseg + (cur - 1), acc);
+      }
+      cur = k0;
+      acc = inf ? xyzz_inf<P>() : xyzz_from_affine<P>(pt);
+    } else if (!inf) {
+      xyzz_madd<P, CALLS>(acc, pt);
+    }
+    e0 = e1; k0 = k1; v0 = v1;
+    e1 = e2; k1 = k2; v1 = v2;
+    b ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (cur != 0) {
+    if (head_open) { store_xyzz<P>(heads + t, acc); head_key = cur; }
+    else store_xyzz<P>(bseg + (cur - 1), acc);
+  }
+  head_keys[t] = head_key;
+}
+
+template <class C>
+void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
+                           const uint32_t* tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
+                           XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
+  size_t nthreads = (size_t)nseg * chunks_per_seg;
+  k_accumulate_rec<C, (C::Fp::L > 8)><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(
+      keys, vals, points, tmp_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
+}
+
+#define ZK_INSTANTIATE_AFF(C)                                                                                             \
+  template int launch_affine_tree<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,   \
+                                     uint32_t, XyzzMem<C::Fp>*, const AffWork&);                                          \
+  template void launch_accumulate_rec<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, \
+                                         size_t, int, int, uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);
+
+#endif  // __CUDACC__
+
+}  // namespace zk

@@ -81,6 +81,70 @@ template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, 
                                           size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
                                           XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys);
 template <class C> int accumulate_resident_threads();
+
+// ---- affine pre-reduction tree (kernels_aff.cuh) ----
+constexpr int AFF_B = 8;          // merges per thread and level
+constexpr int AFF_THREADS = 128;
+constexpr int BINV_G = 4;         // elements per thread in the product trees of the batch inversion
+struct AffWork {          // device workspaces, sized by aff_sizes()
+  uint32_t* tmp;          // temporary affine points
+  uint32_t* pre;          // running products, one per merge of the widest level
+  uint32_t* binv;         // thread totals + batch_invert workspace
+  uint4* st[2];           // block states, ping-pong
+  uint32_t* keys_out;     // records for k_accumulate: 2 * ceil(n / 2^R) per segment
+  uint32_t* vals_out;
+};
+struct AffSizes {
+  size_t tmp_points, pre_elems, binv_elems, st0, st1, rec;
+  uint32_t nrec;          // records per segment after the last level
+};
+// Levels of the batch inversion's product tree: big levels are thread-serial (BINV_GS elements per thread, no
+// redundant work), small ones use warp scans (32 * BINV_G elements per warp: fewer dependent steps).
+constexpr int BINV_GS = 8;
+constexpr size_t BINV_SCAN_BELOW = 32768;
+struct BinvLevel { size_t T; int kind; };   // kind 0 = serial, 1 = warp scan, 2 = top (one warp, the inversion)
+inline int binv_plan(size_t T0, BinvLevel* lv) {
+  int n = 0;
+  size_t T = T0;
+  for (;;) {
+    if (T <= 32 * BINV_G) { lv[n++] = {T, 2}; return n; }
+    if (T > BINV_SCAN_BELOW) { lv[n++] = {T, 0}; T = (T + BINV_GS - 1) / BINV_GS; }
+    else { lv[n++] = {T, 1}; T = (T + 32 * BINV_G - 1) / (32 * BINV_G); }
+  }
+}
+inline size_t binv_workspace_elems(size_t T0) {   // per level: PRE (T), X (T/G + 32, scan levels), next level's elements
+  BinvLevel lv[16];
+  int n = binv_plan(T0, lv);
+  size_t tot = 0;
+  for (int i = 0; i < n; i++) tot += lv[i].T + (lv[i].T + BINV_G - 1) / BINV_G + 32 + (i + 1 < n ? lv[i + 1].T + 32 : 0);
+  return tot;
+}
+inline AffSizes aff_sizes(size_t n, int nseg, int R) {
+  AffSizes z{};
+  size_t nin = n;
+  for (int r = 0; r < R; r++) {
+    size_t nm = (nin + 1) / 2;
+    z.tmp_points += (size_t)nseg * nm;
+    if (r == 0) {
+      z.pre_elems = (size_t)nseg * nm;
+      size_t blocks = ((size_t)nseg * nm + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
+      z.binv_elems = blocks * AFF_THREADS + binv_workspace_elems(blocks * AFF_THREADS) + 64;
+      z.st0 = (size_t)nseg * nm;
+    }
+    if (r == 1) z.st1 = (size_t)nseg * nm;
+    nin = nm;
+  }
+  z.nrec = (uint32_t)(2 * nin);
+  z.rec = (size_t)nseg * z.nrec;
+  return z;
+}
+// R levels of pairwise affine sums over the sorted pairs; leaves w.keys_out / w.vals_out for launch_accumulate_rec.
+template <class C> int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n,
+                                          int nseg, int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w);
+template <class C> void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
+                                              const uint32_t* tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
+                                              uint32_t NB, XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads,
+                                              uint32_t* head_keys);
 template <class C> void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<typename C::Fp>* heads_in,
                                            uint32_t T_in, uint32_t* keys_out, XyzzMem<typename C::Fp>* heads_out, uint32_t T_out,
                                            int nseg, uint32_t NB, XyzzMem<typename C::Fp>* buckets, int last);

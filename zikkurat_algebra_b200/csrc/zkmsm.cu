@@ -36,7 +36,8 @@ namespace {
 
 enum Buf {
   B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
-  B_U0, B_V0, B_U1, B_V1, B_OUT, B_NTT_TABLE, B_COUNT
+  B_U0, B_V0, B_U1, B_V1, B_OUT, B_NTT_TABLE, B_AFF_TMP, B_AFF_PRE, B_AFF_BINV, B_AFF_ST0, B_AFF_ST1, B_AFF_KEYS,
+  B_AFF_VALS, B_COUNT
 };
 constexpr int N_EV = 9;
 constexpr int MAX_DEV = 16;
@@ -193,6 +194,11 @@ struct DeviceGuard {  // run on our device, then give the caller its own current
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// curves whose affine pre-reduction kernels are built (kernels_aff.cuh; <curve>_aff.cu)
+template <class C> struct HasAffineTree { static constexpr bool value = false; };
+template <> struct HasAffineTree<Bn254> { static constexpr bool value = true; };
+template <> struct HasAffineTree<Bls12381> { static constexpr bool value = true; };
+
 int ilog2_floor(size_t x) { int r = 0; while (x > 1) { x >>= 1; r++; } return r; }
 
 // Window width c for signed digits: minimise the Fp-multiplication count of the two throughput phases,
@@ -311,26 +317,50 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // Sorted pairs per thread: every accumulate grid is a whole number of waves of resident threads so that
     // all SMs drain together; about 48 insertions per thread for small problems (several waves), up to 192
     // for big ones (fewer chunk heads to fold afterwards, still >= 12 waves).
-    int chunk;
-    {
+    auto pick_chunk = [&](size_t pairs_total, size_t per_seg) -> int {
       const char* e = getenv("ZKB200_CHUNK");
-      if (e && atoi(e) > 0) {
-        chunk = atoi(e);
-      } else {
-        double target = (double)pairs_max / ((double)resident * 12.0);
-        if (target < 48.0) target = 48.0;
-        if (target > 192.0) target = 192.0;
-        double waves = (double)pairs_max / ((double)resident * target);
-        size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
-        size_t per_seg_threads = ((size_t)resident * nw) / (size_t)nseg;  // threads available to one segment
-        if (per_seg_threads < 1) per_seg_threads = 1;
-        size_t ch = (nmax + per_seg_threads - 1) / per_seg_threads;
-        if (ch < 8) ch = 8;
-        if (ch > 1024) ch = 1024;
-        chunk = (int)ch;
-      }
+      if (e && atoi(e) > 0) return atoi(e);
+      double target = (double)pairs_total / ((double)resident * 12.0);
+      if (target < 48.0) target = 48.0;
+      if (target > 192.0) target = 192.0;
+      double waves = (double)pairs_total / ((double)resident * target);
+      size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
+      size_t per_seg_threads = ((size_t)resident * nw) / (size_t)nseg;  // threads available to one segment
+      if (per_seg_threads < 1) per_seg_threads = 1;
+      size_t ch = (per_seg + per_seg_threads - 1) / per_seg_threads;
+      if (ch < 8) ch = 8;
+      if (ch > 1024) ch = 1024;
+      return (int)ch;
+    };
+    const int chunk = pick_chunk(pairs_max, nmax);
+    // ---- affine pre-reduction (kernels_aff.cuh): R levels of pairwise affine sums in front of k_accumulate ----
+    int R = 0;
+    if constexpr (HasAffineTree<C>::value) {
+      const char* e = getenv("ZKB200_AFFINE");
+      R = e ? atoi(e) : 0;
+      if (R > 12) R = 12;
+      while (R > 0 && (nmax >> R) < 2) R--;
+      if (pairs_max >= ((size_t)1 << 30) || n >= ((size_t)1 << 30)) R = 0;   // 30-bit refs
     }
-    const uint32_t cps_max = (uint32_t)((nmax + chunk - 1) / chunk);
+    AffSizes az{};
+    AffWork aw{};
+    int chunk_rec = chunk;
+    if (R > 0) {
+      az = aff_sizes(nmax, nseg, R);
+      aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)(2 * L) * 4);
+      aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, az.pre_elems * (size_t)L * 4);
+      aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, az.binv_elems * (size_t)L * 4);
+      aw.st[0] = (uint4*)cx.ensure(B_AFF_ST0, az.st0 * 16 + 16);
+      aw.st[1] = (uint4*)cx.ensure(B_AFF_ST1, az.st1 * 16 + 16);
+      aw.keys_out = (uint32_t*)cx.ensure(B_AFF_KEYS, az.rec * 4 + 16);
+      aw.vals_out = (uint32_t*)cx.ensure(B_AFF_VALS, az.rec * 4 + 16);
+      chunk_rec = pick_chunk(az.rec, az.nrec);
+    }
+    uint32_t cps_max = (uint32_t)((nmax + chunk - 1) / chunk);
+    if (R > 0) {
+      uint32_t c2 = (uint32_t)((az.nrec + chunk_rec - 1) / chunk_rec);
+      if (c2 > cps_max) cps_max = c2;
+    }
     Mem* heads = (Mem*)cx.ensure(B_HEADS, (size_t)nseg * cps_max * sizeof(Mem));
     uint32_t* head_keys = (uint32_t*)cx.ensure(B_HEADKEYS, (size_t)nseg * cps_max * 4);
     const size_t cap2 = (size_t)nseg * ((cps_max + FIXUP_FAN - 1) / FIXUP_FAN);
@@ -371,11 +401,25 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         CK(cudaStreamWaitEvent(s, cx.ev_pt[k], 0));
       }
       CK(cudaEventRecord(ge[0], s));
-      const uint32_t cps = (uint32_t)((nk + chunk - 1) / chunk);
-      g_launches++;
       Mem* kb_ = buckets + (size_t)k * slice_stride;
-      launch_accumulate<C>(s, keys[cur], vals[cur], d_points + lo[k] * (size_t)(2 * L), nk, nseg, chunk, cps, NB, kb_, heads,
-                           head_keys);
+      const uint32_t* pts_k = d_points + lo[k] * (size_t)(2 * L);
+      uint32_t cps = 0;
+      if constexpr (HasAffineTree<C>::value) {
+        if (R > 0) {
+          AffSizes zk_ = aff_sizes(nk, nseg, R);
+          g_launches += launch_affine_tree<C>(s, keys[cur], vals[cur], pts_k, nk, nseg, R, NB, kb_, aw);
+          CK(cudaGetLastError());
+          cps = (uint32_t)((zk_.nrec + chunk_rec - 1) / chunk_rec);
+          g_launches++;
+          launch_accumulate_rec<C>(s, aw.keys_out, aw.vals_out, pts_k, aw.tmp, zk_.nrec, nseg, chunk_rec, cps, NB, kb_, heads,
+                                   head_keys);
+        }
+      }
+      if (R == 0) {
+        cps = (uint32_t)((nk + chunk - 1) / chunk);
+        g_launches++;
+        launch_accumulate<C>(s, keys[cur], vals[cur], pts_k, nk, nseg, chunk, cps, NB, kb_, heads, head_keys);
+      }
       CK(cudaGetLastError());
       CK(cudaEventRecord(ge[1], s));
       {  // fold the chunk heads into the buckets: log_FAN(chunks) small levels
