@@ -37,9 +37,13 @@ PRODUCTS_PER_INSERTION = {"bn128": 1360, "bls12_381": 3000}   # 10 Fp mul x (2L^
 # what k_accumulate really executes per insertion: 6 mul + 2 dedicated squarings + 1 fused (a*b + c*d):
 # 6(2L^2+L) + 2(L(L+1)/2 + L^2 + L) + (3L^2 + L)
 EXECUTED_PER_INSERTION = {"bn128": 6 * 136 + 2 * 108 + 200, "bls12_381": 6 * 300 + 2 * 234 + 444}
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_accumulate launch from an `ncu --set full` capture
-# (profiles/*_ncu_k_accumulate_*.txt), keyed by (curve, log2 n); None where no capture exists.
-NCU_TRAFFIC = {("bls12_381", 20): 1.738798e9 + 0.172671e9}   # profiles/r1_e_ncu_k_accumulate_bls12381_2p20.txt
+# one batched-affine addition of the pre-reduction tree (kernels_aff.cuh): 5 mul + 1 squaring
+EXECUTED_PER_AFFINE_ADD = {"bn128": 5 * 136 + 108, "bls12_381": 5 * 300 + 234}
+# dram__bytes_read.sum + dram__bytes_write.sum of the bucket-accumulation phase from an `ncu --set full` capture, keyed by
+# (curve, log2 n, affine levels); None where no capture exists.
+#   R = 0: ONE k_accumulate launch                      profiles/r1_e_ncu_k_accumulate_bls12381_2p20.txt
+#   R = 3: all kernels of the phase summed (tree + records)   profiles/r1_f_ncu_accumulate_phase_bls12381_2p20.txt
+NCU_TRAFFIC = {("bls12_381", 20, 0): 1.738798e9 + 0.172671e9}
 METRIC = "G1 MSM throughput"
 UNIT = "points/s"
 
@@ -300,19 +304,30 @@ def main():
     peak = props.multi_processor_count * 4 * 32 / 4.0 * sm_mhz * 1e6
     passes = (stats["window"] + 7) // 8
     sort_bytes = stats["insertions"] * 20 * passes
-    traffic = NCU_TRAFFIC.get((curve, logn))
-    roofline = {"bound": "imad", "kernel": "k_accumulate", "achieved": achieved / 1e9, "peak": peak / 1e9,
+    R = int(stats.get("affine_levels", 0))
+    traffic = NCU_TRAFFIC.get((curve, logn, R))
+    # products really executed by the phase: with R levels of batched-affine pre-reduction, level r adds (at most)
+    # insertions / 2^(r+1) pairs at 5M+1S each and the XYZZ insertion (6M+2S+fused) is left for insertions / 2^R records
+    ins = stats["insertions"]
+    executed = sum(ins / 2 ** (r + 1) for r in range(R)) * EXECUTED_PER_AFFINE_ADD[curve] + ins / 2 ** R * EXECUTED_PER_INSERTION[curve]
+    kernel = "k_accumulate" if R == 0 else (f"bucket accumulation phase: {R} levels of batched-affine pre-reduction "
+                                            "(k_aff_prod, inversion chain, k_aff_add) + k_accumulate_rec")
+    note = ("achieved/frac use SURVEY.md 8d's algorithmic 10 Fp mul per insertion; the kernel executes fewer products "
+            "(fused Y3 reduction, dedicated squarings)")
+    if R:
+        note += (f"; with {R} affine levels most additions cost 5M+1S instead of 8M+2S, so frac can exceed 1 -- "
+                 "frac_of_pipe_peak is the utilisation of the IMAD pipe by the products really executed")
+    roofline = {"bound": "imad", "kernel": kernel, "achieved": achieved / 1e9, "peak": peak / 1e9,
                 "unit": "Gproducts/s (32x32->64-bit multiply-adds)", "frac": achieved / peak,
                 "peak_source": f"IMAD pipe: {props.multi_processor_count} SM x 4 SMSP x 32 lanes / 4 cycles per IMAD.WIDE x "
                                f"{sm_mhz:.0f} MHz (SM clock sampled during the timed region); cross-check: ncu "
                                "sm__pipe_fmaheavy_cycles_active (profiles/), zkb200_imad_peak carry-chain probe on this GPU = "
                                f"{probe / 1e9:.0f} Gproducts/s",
                 "probe_gproducts": probe / 1e9,
-                "executed": {"products_per_insertion": EXECUTED_PER_INSERTION[curve],
-                             "gproducts_per_s": stats["insertions"] * EXECUTED_PER_INSERTION[curve] / t_acc / 1e9,
-                             "frac_of_pipe_peak": stats["insertions"] * EXECUTED_PER_INSERTION[curve] / t_acc / peak,
-                             "note": "achieved/frac use SURVEY.md 8d's algorithmic 10 Fp mul per insertion; the kernel "
-                                     "executes fewer products (fused Y3 reduction, dedicated squarings)"},
+                "executed": {"products_per_insertion": executed / ins, "affine_levels": R,
+                             "gproducts_per_s": executed / t_acc / 1e9,
+                             "frac_of_pipe_peak": executed / t_acc / peak,
+                             "note": note},
                 "per_launch": {"insertions": stats["insertions"], "products_per_insertion": ppi, "window_c": stats["window"],
                                "nwindows": stats["nwindows"], "avg_ms": t_acc * 1e3,
                                "algorithmic_gather_bytes": stats["insertions"] * (2 * L * 8 + 8)},

@@ -175,6 +175,8 @@ void zkb200_set_devices(const int *devices, int count);
  *  [6] reduce  [7] tail + d2h   [8] total on the compute stream.
  * Also: window width c, number of windows W, insertions n*W, of the same call. */
 void zkb200_last_stats(float phase_ms[9], int *window_c, int *nwindows, long long *insertions);
+/* levels of the batched-affine pre-reduction the last MSM on the current device used (0 = plain XYZZ accumulation) */
+int zkb200_last_affine_levels(void);
 
 /* Register-resident integer-multiply throughput probe: returns 32x32-bit products per second of the
  * whole GPU for kind 0 = mad.lo/madc.hi carry chains (as used by the field code), 1 = mad.wide.u32,

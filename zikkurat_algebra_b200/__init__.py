@@ -49,7 +49,7 @@ EXTRA_SYMBOLS = ([f"{c}_G2_proj_batch_{d}_affine" for c in ("bn128", "bls12_381"
                  [f"{c}_{g}_out_slow_reference" for c in ("bn128", "bls12_381")
                   for g in ("G1_proj_MSM_std_coeff_proj", "G1_jac_MSM_std_coeff_jac", "G2_proj_MSM_std_coeff_proj")])
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
-                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt", "zkb200_device_upload", "zkb200_device_free"]
+                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt", "zkb200_device_upload", "zkb200_device_free", "zkb200_last_affine_levels"]
 
 _U64P = ctypes.POINTER(ctypes.c_uint64)
 _lib: Optional[ctypes.CDLL] = None
@@ -299,8 +299,10 @@ def last_stats() -> dict:
     c, w, ins = ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
     lib().zkb200_last_stats(ms, ctypes.byref(c), ctypes.byref(w), ctypes.byref(ins))
     names = ["h2d_scalars", "recode", "sort", "wait_points", "accumulate", "fixup", "reduce", "tail_d2h", "total"]
+    L = lib()
+    L.zkb200_last_affine_levels.restype = ctypes.c_int
     return {"phase_ms": dict(zip(names, [float(x) for x in ms])), "window": c.value, "nwindows": w.value,
-            "insertions": ins.value}
+            "insertions": ins.value, "affine_levels": int(L.zkb200_last_affine_levels())}
 
 
 def imad_peak(kind: int = 0, iters: int = 2000) -> float:

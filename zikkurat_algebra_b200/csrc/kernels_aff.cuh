@@ -140,64 +140,124 @@ k_aff_prod(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
 // ---- step 3: finish the additions, write sums and merged states ---------------------------------------------
 // totinv[t] = inverse of thread t's total.  Sums go to tmp[tmp_off + m].  Output: st_out[m] (uint4 states) or,
 // on the LAST level, split (key, ref) records for k_accumulate: 2 per block, head slot 0 when the block is one run.
-template <class C, bool LEVEL0, bool LAST>
+// The operands of merge j-1 (two points and the stored running product, 5 x field element) travel into this
+// thread's shared-memory slot with cp.async while merge j is being computed, exactly like the point gather of
+// k_accumulate.  Slot layout [buffer][16-byte word][thread]: conflict-free.
+template <class P>
+constexpr int aff_stage_words() { return 2 * ((2 * P::L) / 4) + P::L / 4; }
+template <class P>
+constexpr size_t aff_stage_bytes() { return (size_t)2 * aff_stage_words<P>() * AFF_THREADS * 16; }
+
+template <class C, bool LEVEL0, bool LAST, bool CALLS>
 __global__ void __launch_bounds__(AFF_THREADS)
 k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
           uint32_t nm, uint32_t total, const uint32_t* points, uint32_t* tmp, uint32_t tmp_off, const uint32_t* __restrict__ pre,
           const uint32_t* __restrict__ totinv, uint4* __restrict__ st_out, uint32_t* __restrict__ keys_out,
           uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets) {
   using P = typename C::Fp;
-  constexpr bool CALLS = (P::L > 8);
+  constexpr int PW = (2 * P::L) / 4, FW = P::L / 4, NW = 2 * PW + FW;
+  extern __shared__ uint4 aff_stage[];   // [2][NW][AFF_THREADS]
   const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * AFF_B);
   Fe<P> r = ld_fe<P>(totinv + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L);
-  for (int j = AFF_B - 1; j >= 0; j--) {
+  // fetch(j): read the two blocks of merge j and start the copies of its operands
+  auto fetch = [&](int j, int buf, AffPair& a, uint32_t& seg, uint32_t& i) -> bool {
     const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
-    if (m >= total) continue;
-    const uint32_t seg = m / nm, i = m - seg * nm;
-    AffPair a = aff_read_pair<LEVEL0>(keys, vals, st_in, nin, seg, i);
-    AffPlan pl = aff_plan(a.Lhk, a.Lhr, a.Ltk, a.Ltr, a.Rhk, a.Rhr, a.Rtk, a.Rtr);
-    XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
-    if (pl.add) {
-      bool i1, i2;
-      Affine<P> p1 = aff_load<P>(points, tmp, a.Ltr, i1), p2 = aff_load<P>(points, tmp, a.Rhr, i2);
-      Fe<P> d;
-      const int cls = aff_classify<P>(p1, i1, p2, i2, d);
-      Affine<P> s = p1;
-      bool sinf = false;
-      if (cls >= AFF_ADD) {
-        Fe<P> dinv = aff_mul<P, CALLS>(r, ld_fe<P>(pre + (size_t)m * P::L));
-        r = aff_mul<P, CALLS>(r, d);
-        s = aff_finish<P, CALLS>(cls, p1, p2, dinv);
-      } else if (cls == AFF_COPY2) {
-        s = p2;
-      } else if (cls == AFF_INF) {
-        sinf = true;
-      }
-      if (pl.sum_key != 0) aff_to_bucket<P>(bseg + (pl.sum_key - 1), s, sinf);
-      else aff_store<P>(tmp, (size_t)tmp_off + m, s, sinf);
-      const uint32_t sref = AFF_TEMP | (tmp_off + m);
-      if (pl.hr == AFF_SUM) pl.hr = sref;
-      if (pl.tr == AFF_SUM) pl.tr = sref;
-    } else {
+    if (j < 0 || m >= total) return false;
+    seg = m / nm;
+    i = m - seg * nm;
+    a = aff_read_pair<LEVEL0>(keys, vals, st_in, nin, seg, i);
+    if (a.Ltk == a.Rhk && a.Ltk != 0) {
+      const uint4* s1 = reinterpret_cast<const uint4*>(aff_addr<P>(points, tmp, a.Ltr));
+      const uint4* s2 = reinterpret_cast<const uint4*>(aff_addr<P>(points, tmp, a.Rhr));
+      const uint4* s3 = reinterpret_cast<const uint4*>(pre + (size_t)m * P::L);
+      uint4* dst = aff_stage + (size_t)buf * NW * AFF_THREADS + threadIdx.x;
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
-        if (pl.st_key[k] != 0) {
-          bool inf;
-          Affine<P> p = aff_load<P>(points, tmp, pl.st_ref[k], inf);
-          aff_to_bucket<P>(bseg + (pl.st_key[k] - 1), p, inf);
+      for (int w = 0; w < NW; w++) {
+        const uint4* src = w < PW ? s1 + w : (w < 2 * PW ? s2 + (w - PW) : s3 + (w - 2 * PW));
+        unsigned d = (unsigned)__cvta_generic_to_shared(dst + (size_t)w * AFF_THREADS);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+      }
+    }
+    return true;
+  };
+  auto staged = [&](int buf, int w0, uint32_t* out, int nwords) {
+    const uint4* src = aff_stage + (size_t)buf * NW * AFF_THREADS + threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < nwords; w++) {
+      uint4 q = src[(size_t)(w0 + w) * AFF_THREADS];
+      out[4 * w] = q.x; out[4 * w + 1] = q.y; out[4 * w + 2] = q.z; out[4 * w + 3] = q.w;
+    }
+  };
+  AffPair a, an;
+  uint32_t seg = 0, i = 0, segn = 0, in_ = 0;
+  bool have = fetch(AFF_B - 1, (AFF_B - 1) & 1, a, seg, i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 1
+  for (int j = AFF_B - 1; j >= 0; j--) {
+    const bool have_next = fetch(j - 1, (j - 1) & 1, an, segn, in_);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    if (have) {
+      const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
+      AffPlan pl = aff_plan(a.Lhk, a.Lhr, a.Ltk, a.Ltr, a.Rhk, a.Rhr, a.Rtk, a.Rtr);
+      XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
+      if (pl.add) {
+        Affine<P> p1, p2;
+        {
+          uint32_t w32[2 * P::L];
+          staged(j & 1, 0, w32, PW);
+#pragma unroll
+          for (int k = 0; k < P::L; k++) { p1.x.l[k] = w32[k]; p1.y.l[k] = w32[P::L + k]; }
+          staged(j & 1, PW, w32, PW);
+#pragma unroll
+          for (int k = 0; k < P::L; k++) { p2.x.l[k] = w32[k]; p2.y.l[k] = w32[P::L + k]; }
+        }
+        const bool i1 = affine_is_inf<P>(p1), i2 = affine_is_inf<P>(p2);
+        if ((a.Ltr >> 31) && !i1) p1.y = fe_neg<P>(p1.y);
+        if ((a.Rhr >> 31) && !i2) p2.y = fe_neg<P>(p2.y);
+        Fe<P> d;
+        const int cls = aff_classify<P>(p1, i1, p2, i2, d);
+        Affine<P> s = p1;
+        bool sinf = false;
+        if (cls >= AFF_ADD) {
+          Fe<P> pr;
+          staged(j & 1, 2 * PW, pr.l, FW);
+          Fe<P> dinv = aff_mul<P, CALLS>(r, pr);
+          r = aff_mul<P, CALLS>(r, d);
+          s = aff_finish<P, CALLS>(cls, p1, p2, dinv);
+        } else if (cls == AFF_COPY2) {
+          s = p2;
+        } else if (cls == AFF_INF) {
+          sinf = true;
+        }
+        if (pl.sum_key != 0) aff_to_bucket<P>(bseg + (pl.sum_key - 1), s, sinf);
+        else aff_store<P>(tmp, (size_t)tmp_off + m, s, sinf);
+        const uint32_t sref = AFF_TEMP | (tmp_off + m);
+        if (pl.hr == AFF_SUM) pl.hr = sref;
+        if (pl.tr == AFF_SUM) pl.tr = sref;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (pl.st_key[k] != 0) {
+            bool inf;
+            Affine<P> p = aff_load<P>(points, tmp, pl.st_ref[k], inf);
+            aff_to_bucket<P>(bseg + (pl.st_key[k] - 1), p, inf);
+          }
         }
       }
+      if (LAST) {
+        const size_t o = ((size_t)seg * nm + i) * 2;
+        keys_out[o] = pl.hk == pl.tk ? 0u : pl.hk;
+        vals_out[o] = pl.hk == pl.tk ? 0u : pl.hr;
+        keys_out[o + 1] = pl.tk;
+        vals_out[o + 1] = pl.tk == 0 ? 0u : pl.tr;
+      } else {
+        st_out[m] = make_uint4(pl.hk, pl.hr, pl.tk, pl.tr);
+      }
     }
-    if (LAST) {
-      const size_t o = ((size_t)seg * nm + i) * 2;
-      keys_out[o] = pl.hk == pl.tk ? 0u : pl.hk;
-      vals_out[o] = pl.hk == pl.tk ? 0u : pl.hr;
-      keys_out[o + 1] = pl.tk;
-      vals_out[o + 1] = pl.tk == 0 ? 0u : pl.tr;
-    } else {
-      st_out[m] = make_uint4(pl.hk, pl.hr, pl.tk, pl.tr);
-    }
+    have = have_next; a = an; seg = segn; i = in_;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- step 2: batch inversion of an array of field elements ------------------------------------------------
@@ -355,41 +415,6 @@ int batch_invert(cudaStream_t s, const uint32_t* E0, size_t T0, uint32_t* ws, ui
   return launches;
 }
 
-// ---- host driver: R levels over sorted pairs ------------------------------------------------------------------
-template <class C>
-int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int nseg,
-                       int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w) {
-  using P = typename C::Fp;
-  int launches = 0;
-  uint32_t nin = (uint32_t)n, tmp_off = 0;
-  for (int r = 0; r < R; r++) {
-    const uint32_t nm = (nin + 1) / 2;
-    const uint32_t total = (uint32_t)nseg * nm;
-    const unsigned blocks = (total + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
-    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1];
-    uint4* st_out = w.st[r & 1];
-    uint32_t* tot = w.binv;
-    const size_t T0 = (size_t)blocks * AFF_THREADS;
-    if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, s>>>(keys, vals, st_in, nin, nm, total, points, w.tmp, w.pre, tot);
-    else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, s>>>(keys, vals, st_in, nin, nm, total, points, w.tmp, w.pre, tot);
-    uint32_t* inv = nullptr;
-    launches += 1 + batch_invert<P>(s, tot, T0, tot + T0 * P::L, &inv);
-    const bool last = r == R - 1;
-#define ZK_AFF_ADD(L0, LA)                                                                                                  \
-  k_aff_add<C, L0, LA><<<blocks, AFF_THREADS, 0, s>>>(keys, vals, st_in, nin, nm, total, points, w.tmp, tmp_off, w.pre, inv, \
-                                                      st_out, w.keys_out, w.vals_out, NB, buckets)
-    if (r == 0 && last) ZK_AFF_ADD(true, true);
-    else if (r == 0) ZK_AFF_ADD(true, false);
-    else if (last) ZK_AFF_ADD(false, true);
-    else ZK_AFF_ADD(false, false);
-#undef ZK_AFF_ADD
-    launches++;
-    tmp_off += total;
-    nin = nm;
-  }
-  return launches;
-}
-
 // ---- XYZZ accumulation of the surviving records -----------------------------------------------------------------
 // k_accumulate (kernels_acc.cuh) over the record list of the last tree level: `chunk` record SLOTS per thread, empty
 // slots (key 0) skipped per lane so that every trip of the loop adds a real record; a value with bit 30 set names a
@@ -431,14 +456,15 @@ k_accumulate_rec(const uint32_t* __restrict__ keys, const uint32_t* __restrict__
   asm volatile("cp.async.commit_group;" ::: "memory");
   if (e1 < end) { k1 = kp[e1]; v1 = vp[e1]; }
   int b = 0;
-  while (e0 < end) {
+  // next record of this thread (point fetched through the cp.async pipeline); false when the chunk is exhausted
+  auto step = [&](Affine<P>& pt, bool& inf, uint32_t& key) -> bool {
+    if (e0 >= end) return false;
     size_t e2 = end;
     uint32_t k2 = 0, v2 = 0;
     if (e1 < end) { prefetch(b ^ 1, v1); e2 = skip(e1 + 1); }
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (e2 < end) { k2 = kp[e2]; v2 = vp[e2]; }
     asm volatile("cp.async.wait_group 1;" ::: "memory");
-    Affine<P> pt;
     {
       uint32_t w32[2 * P::L];
 #pragma unroll
@@ -449,22 +475,31 @@ k_accumulate_rec(const uint32_t* __restrict__ keys, const uint32_t* __restrict__
 #pragma unroll
       for (int k = 0; k < P::L; k++) { pt.x.l[k] = w32[k]; pt.y.l[k] = w32[P::L + k]; }
     }
-    const bool inf = affine_is_inf<P>(pt);
+    inf = affine_is_inf<P>(pt);
     Fe<P> ny = fe_neg<P>(pt.y);
     if (v0 >> 31) pt.y = ny;
-    if (k0 != cur) {
+    key = k0;
+    e0 = e1; k0 = k1; v0 = v1;
+    e1 = e2; k1 = k2; v1 = v2;
+    b ^= 1;
+    return true;
+  };
+  for (;;) {
+    Affine<P> pt;
+    bool inf = false, got;
+    uint32_t key = 0;
+    // records that open a new run are cheap (store the finished sum, restart from the point): a lane works
+    // through them here, so that the warp meets again at the expensive addition below
+    while ((got = step(pt, inf, key)) && key != cur) {
       if (cur != 0) {
         if (head_open) { store_xyzz<P>(heads + t, acc); head_key = cur; head_open = false; }
         else store_xyzz<P>(bseg + (cur - 1), acc);
       }
-      cur = k0;
+      cur = key;
       acc = inf ? xyzz_inf<P>() : xyzz_from_affine<P>(pt);
-    } else if (!inf) {
-      xyzz_madd<P, CALLS>(acc, pt);
     }
-    e0 = e1; k0 = k1; v0 = v1;
-    e1 = e2; k1 = k2; v1 = v2;
-    b ^= 1;
+    if (!got) break;
+    if (!inf) xyzz_madd<P, CALLS>(acc, pt);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (cur != 0) {
@@ -483,9 +518,119 @@ void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t*
       keys, vals, points, tmp_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
 }
 
+// ---- host driver: R levels over sorted pairs, then the records ------------------------------------------------------
+template <class C>
+int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int nseg,
+                       int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w, const AffStreams& as,
+                       int chunk_rec, uint32_t cps, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
+  using P = typename C::Fp;
+  int launches = 0;
+  int inl = -1;   // code shape of the additions: multiplications inlined (1) or out of line (0); $ZKB200_AFF_INLINE
+  if (inl < 0) { const char* e = getenv("ZKB200_AFF_INLINE"); inl = e ? atoi(e) : (P::L > 8 ? 0 : 1); }
+  const size_t smem = aff_stage_bytes<P>();
+  const int G = (as.groups == 2 && nseg >= 2) ? 2 : 1;
+  cudaStream_t big[2] = {s, s}, chain[2] = {s, s};
+  int seg0[2] = {0, 0}, segs[2] = {nseg, 0};
+  size_t tmp_base[2] = {0, 0}, binv_base[2] = {0, 0};
+  if (G == 2) {
+    cudaEventRecord(as.ev_start, s);
+    for (int g = 0; g < 2; g++) {
+      big[g] = as.big[g];
+      chain[g] = as.chain[g];
+      int s1;
+      aff_group_range(nseg, 2, g, seg0[g], s1);
+      segs[g] = s1 - seg0[g];
+      cudaStreamWaitEvent(big[g], as.ev_start, 0);
+    }
+    AffSizes z0 = aff_sizes(n, segs[0], R);
+    tmp_base[1] = z0.tmp_points;
+    binv_base[1] = z0.binv_elems + 64;
+  }
+  // per level: blocks per segment going in, merges per segment
+  uint32_t nin_l[16], nm_l[16];
+  {
+    uint32_t nin = (uint32_t)n;
+    for (int r = 0; r < R; r++) { nin_l[r] = nin; nm_l[r] = (nin + 1) / 2; nin = nm_l[r]; }
+  }
+  size_t lvl_off[2] = {tmp_base[0], tmp_base[1]};   // where the current level's sums start in the temporary array
+  uint32_t* inv[2] = {nullptr, nullptr};
+  // step 1 + 2 of level r for group g: running products on the group's stream, inversion chain on its chain stream
+  auto do_prod = [&](int g, int r) {
+    const uint32_t nin = nin_l[r], nm = nm_l[r], total = (uint32_t)segs[g] * nm;
+    const unsigned blocks = (total + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
+    const uint32_t* kg = keys + (size_t)seg0[g] * n;
+    const uint32_t* vg = vals + (size_t)seg0[g] * n;
+    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * nin;
+    uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
+    uint32_t* tot = w.binv + binv_base[g] * P::L;
+    const size_t T0 = (size_t)blocks * AFF_THREADS;
+    if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot);
+    else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot);
+    launches++;
+    if (G == 2) { cudaEventRecord(as.ev_a[g], big[g]); cudaStreamWaitEvent(chain[g], as.ev_a[g], 0); }
+    launches += batch_invert<P>(chain[g], tot, T0, tot + T0 * P::L, &inv[g]);
+    if (G == 2) { cudaEventRecord(as.ev_c[g], chain[g]); cudaStreamWaitEvent(big[g], as.ev_c[g], 0); }
+  };
+  // step 3 of level r for group g
+  auto do_add = [&](int g, int r) {
+    const uint32_t nin = nin_l[r], nm = nm_l[r], total = (uint32_t)segs[g] * nm;
+    const unsigned blocks = (total + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
+    const bool last = r == R - 1;
+    const uint32_t* kg = keys + (size_t)seg0[g] * n;
+    const uint32_t* vg = vals + (size_t)seg0[g] * n;
+    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * nin;
+    uint4* st_out = w.st[r & 1] + (size_t)seg0[g] * nm;
+    uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
+    uint32_t* ko = w.keys_out + (size_t)seg0[g] * 2 * nm;
+    uint32_t* vo = w.vals_out + (size_t)seg0[g] * 2 * nm;
+    XyzzMem<P>* bg = buckets + (size_t)seg0[g] * NB;
+    const uint32_t tmp_off = (uint32_t)lvl_off[g];
+#define ZK_AFF_ADD(L0, LA)                                                                                                    \
+  do {                                                                                                                        \
+    if (inl) {                                                                                                                \
+      cudaFuncSetAttribute(k_aff_add<C, L0, LA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+      k_aff_add<C, L0, LA, false><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off, \
+                                                                         pre, inv[g], st_out, ko, vo, NB, bg);                \
+    } else {                                                                                                                  \
+      cudaFuncSetAttribute(k_aff_add<C, L0, LA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+      k_aff_add<C, L0, LA, true><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off,  \
+                                                                        pre, inv[g], st_out, ko, vo, NB, bg);                 \
+    }                                                                                                                         \
+  } while (0)
+    if (r == 0 && last) ZK_AFF_ADD(true, true);
+    else if (r == 0) ZK_AFF_ADD(true, false);
+    else if (last) ZK_AFF_ADD(false, true);
+    else ZK_AFF_ADD(false, false);
+#undef ZK_AFF_ADD
+    launches++;
+    lvl_off[g] += total;
+  };
+  const uint32_t nrec = 2 * nm_l[R - 1];   // surviving record slots per segment
+  auto do_records = [&](int g) {
+    launch_accumulate_rec<C>(big[g], w.keys_out + (size_t)seg0[g] * nrec, w.vals_out + (size_t)seg0[g] * nrec, points, w.tmp, nrec,
+                             segs[g], chunk_rec, cps, NB, buckets + (size_t)seg0[g] * NB, heads + (size_t)seg0[g] * cps,
+                             head_keys + (size_t)seg0[g] * cps);
+    launches++;
+    if (G == 2) { cudaEventRecord(as.ev_done[g], big[g]); cudaStreamWaitEvent(s, as.ev_done[g], 0); }
+  };
+  // Enqueue order = execution order of the big kernels (equal-priority streams drain first come first served):
+  // a group's next running products follow its additions immediately, so that its inversion chain runs under the
+  // OTHER group's additions.  Only the very first chain has just the other group's running products to hide behind.
+  for (int g = 0; g < G; g++) do_prod(g, 0);
+  for (int r = 0; r < R; r++) {
+    for (int g = 0; g < G; g++) {
+      do_add(g, r);
+      if (r + 1 < R) do_prod(g, r + 1);
+      else do_records(g);
+    }
+  }
+  return launches;
+}
+
 #define ZK_INSTANTIATE_AFF(C)                                                                                             \
   template int launch_affine_tree<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,   \
-                                     uint32_t, XyzzMem<C::Fp>*, const AffWork&);                                          \
+                                     uint32_t, XyzzMem<C::Fp>*, const AffWork&, const AffStreams&, int, uint32_t,         \
+                                     XyzzMem<C::Fp>*, uint32_t*);                                                         \
   template void launch_accumulate_rec<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, \
                                          size_t, int, int, uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);
 

@@ -83,7 +83,7 @@ template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, 
 template <class C> int accumulate_resident_threads();
 
 // ---- affine pre-reduction tree (kernels_aff.cuh) ----
-constexpr int AFF_B = 8;          // merges per thread and level
+constexpr int AFF_B = 16;         // merges per thread and level
 constexpr int AFF_THREADS = 128;
 constexpr int BINV_G = 4;         // elements per thread in the product trees of the batch inversion
 struct AffWork {          // device workspaces, sized by aff_sizes()
@@ -138,9 +138,33 @@ inline AffSizes aff_sizes(size_t n, int nseg, int R) {
   z.rec = (size_t)nseg * z.nrec;
   return z;
 }
-// R levels of pairwise affine sums over the sorted pairs; leaves w.keys_out / w.vals_out for launch_accumulate_rec.
+// Optional second lane for the tree: the segments are cut into `groups` groups that run on their own streams, the
+// latency-bound inversion chains on high-priority streams, so that one group's chain runs under the other group's
+// additions instead of leaving the GPU idle.  groups = 1: everything on the caller's stream.
+struct AffStreams {
+  int groups;
+  cudaStream_t big[2], chain[2];
+  cudaEvent_t ev_a[2], ev_c[2], ev_done[2], ev_start;
+};
+inline void aff_group_range(int nseg, int groups, int g, int& s0, int& s1) {
+  s0 = (int)((long long)nseg * g / groups);
+  s1 = (int)((long long)nseg * (g + 1) / groups);
+}
+inline size_t aff_binv_elems_total(size_t n, int nseg, int R, int groups) {
+  size_t tot = 0;
+  for (int g = 0; g < groups; g++) {
+    int s0, s1;
+    aff_group_range(nseg, groups, g, s0, s1);
+    tot += aff_sizes(n, s1 - s0, R).binv_elems + 64;
+  }
+  return tot;
+}
+// R levels of pairwise affine sums over the sorted pairs, then the XYZZ accumulation of the surviving records
+// (chunk_rec record slots per thread, cps threads per segment; heads / head_keys as for launch_accumulate).
 template <class C> int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n,
-                                          int nseg, int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w);
+                                          int nseg, int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w,
+                                          const AffStreams& as, int chunk_rec, uint32_t cps, XyzzMem<typename C::Fp>* heads,
+                                          uint32_t* head_keys);
 template <class C> void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
                                               const uint32_t* tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
                                               uint32_t NB, XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads,

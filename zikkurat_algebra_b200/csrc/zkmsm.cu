@@ -44,7 +44,7 @@ constexpr int MAX_DEV = 16;
 
 struct Stats {
   float ms[9] = {0};
-  int c = 0, W = 0, slices = 1;
+  int c = 0, W = 0, slices = 1, aff_levels = 0;
   bool have_phases = false;
   bool slice_ran[8] = {false};
   long long insertions = 0;
@@ -55,6 +55,7 @@ struct DeviceCtx {
   std::atomic<bool> ready{false};
   int dev = 0;
   cudaStream_t s_main = nullptr, s_copy = nullptr;
+  AffStreams aff{};           // second lane of the affine pre-reduction (kernels_aff.cuh)
   cudaEvent_t ev[N_EV + 1] = {nullptr};
   cudaEvent_t gev[6 * 8] = {nullptr};  // per input slice: accumulate start/end, fix-up end, recode start, sort end, recode end
   cudaEvent_t ev_sc[8] = {nullptr}, ev_pt[8] = {nullptr};   // per input slice: scalars / points have arrived
@@ -125,6 +126,19 @@ DeviceCtx& get_ctx(int d = -1) {
       cx.dev = d;
       CK(cudaStreamCreateWithFlags(&cx.s_main, cudaStreamNonBlocking));
       CK(cudaStreamCreateWithFlags(&cx.s_copy, cudaStreamNonBlocking));
+      {
+        int lo_pri = 0, hi_pri = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        cx.aff.groups = 2;
+        for (int g = 0; g < 2; g++) {
+          CK(cudaStreamCreateWithPriority(&cx.aff.big[g], cudaStreamNonBlocking, lo_pri));
+          CK(cudaStreamCreateWithPriority(&cx.aff.chain[g], cudaStreamNonBlocking, hi_pri));
+          CK(cudaEventCreateWithFlags(&cx.aff.ev_a[g], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&cx.aff.ev_c[g], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&cx.aff.ev_done[g], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&cx.aff.ev_start, cudaEventDisableTiming));
+      }
       for (int i = 0; i < 6 * 8; i++) CK(cudaEventCreate(&cx.gev[i]));
       for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
       for (int i = 0; i < 8; i++) {
@@ -336,20 +350,41 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // ---- affine pre-reduction (kernels_aff.cuh): R levels of pairwise affine sums in front of k_accumulate ----
     int R = 0;
     if constexpr (HasAffineTree<C>::value) {
+      // Levels: the tree pays while runs of equal keys are long (avg run = n / NB) and the problem is big enough
+      // to hide the per-level inversion chains; measured on B200 (profiles/r1_notes.md).  Override: $ZKB200_AFFINE.
       const char* e = getenv("ZKB200_AFFINE");
-      R = e ? atoi(e) : 0;
+      if (e) {
+        R = atoi(e);
+      } else if (L > 8 ? nmax >= ((size_t)1 << 19) : (nmax >= ((size_t)1 << 21) && nmax < ((size_t)1 << 23))) {
+        // 12 limbs: -12 % (2^20) .. -17 % (2^22, 2^24) of the whole MSM; 8 limbs: -3 % around 2^22, a loss at 2^24
+        // (the cheaper multiplication leaves the tree's extra memory traffic exposed)
+        R = ilog2_floor(nmax / NB + 1) - 2;
+        if (pairs_max >= ((size_t)1 << 26)) R++;
+        if (R > 5) R = 5;
+      }
+      if (R < 0) R = 0;
       if (R > 12) R = 12;
       while (R > 0 && (nmax >> R) < 2) R--;
       if (pairs_max >= ((size_t)1 << 30) || n >= ((size_t)1 << 30)) R = 0;   // 30-bit refs
+      if (R > 0) {   // workspace guard: temporary points + running products
+        AffSizes z = aff_sizes(nmax, nseg, R);
+        if ((z.tmp_points * 2 + z.pre_elems) * (size_t)L * 4 > ((size_t)48 << 30)) R = 0;
+      }
     }
+    st.aff_levels = R;
     AffSizes az{};
     AffWork aw{};
+    AffStreams as = cx.aff;
+    {
+      const char* e = getenv("ZKB200_AFF_GROUPS");
+      as.groups = (e ? atoi(e) : 2) == 2 ? 2 : 1;
+    }
     int chunk_rec = chunk;
     if (R > 0) {
       az = aff_sizes(nmax, nseg, R);
       aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)(2 * L) * 4);
       aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, az.pre_elems * (size_t)L * 4);
-      aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, az.binv_elems * (size_t)L * 4);
+      aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, (aff_binv_elems_total(nmax, nseg, R, 2) + az.binv_elems) * (size_t)L * 4);
       aw.st[0] = (uint4*)cx.ensure(B_AFF_ST0, az.st0 * 16 + 16);
       aw.st[1] = (uint4*)cx.ensure(B_AFF_ST1, az.st1 * 16 + 16);
       aw.keys_out = (uint32_t*)cx.ensure(B_AFF_KEYS, az.rec * 4 + 16);
@@ -407,12 +442,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if constexpr (HasAffineTree<C>::value) {
         if (R > 0) {
           AffSizes zk_ = aff_sizes(nk, nseg, R);
-          g_launches += launch_affine_tree<C>(s, keys[cur], vals[cur], pts_k, nk, nseg, R, NB, kb_, aw);
-          CK(cudaGetLastError());
           cps = (uint32_t)((zk_.nrec + chunk_rec - 1) / chunk_rec);
-          g_launches++;
-          launch_accumulate_rec<C>(s, aw.keys_out, aw.vals_out, pts_k, aw.tmp, zk_.nrec, nseg, chunk_rec, cps, NB, kb_, heads,
-                                   head_keys);
+          g_launches += launch_affine_tree<C>(s, keys[cur], vals[cur], pts_k, nk, nseg, R, NB, kb_, aw, as, chunk_rec, cps, heads,
+                                              head_keys);
         }
       }
       if (R == 0) {
@@ -841,6 +873,12 @@ void zkb200_last_stats(float phase_ms[9], int* window_c, int* nwindows, long lon
   if (window_c) *window_c = cx.stats.c;
   if (nwindows) *nwindows = cx.stats.W;
   if (insertions) *insertions = cx.stats.insertions;
+}
+
+int zkb200_last_affine_levels(void) {
+  DeviceCtx& cx = get_ctx();
+  std::lock_guard<std::mutex> lk(cx.mu);
+  return cx.stats.aff_levels;
 }
 
 double zkb200_imad_peak(int kind, int iters) {
