@@ -106,12 +106,13 @@ template <class C, bool LEVEL0>
 __global__ void __launch_bounds__(AFF_THREADS)
 k_aff_prod(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
            uint32_t nm, uint32_t total, const uint32_t* points, const uint32_t* tmp, uint32_t* __restrict__ pre,
-           uint32_t* __restrict__ tot) {
+           uint32_t* __restrict__ tot, int B) {
   using P = typename C::Fp;
   constexpr bool CALLS = (P::L > 8);
-  const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * AFF_B);
+  const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * B);
   Fe<P> run = fe_one<P>();
-  for (int j = 0; j < AFF_B; j++) {
+#pragma unroll 1
+  for (int j = 0; j < B; j++) {
     const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
     if (m >= total) break;
     const uint32_t seg = m / nm, i = m - seg * nm;
@@ -153,11 +154,11 @@ __global__ void __launch_bounds__(AFF_THREADS)
 k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
           uint32_t nm, uint32_t total, const uint32_t* points, uint32_t* tmp, uint32_t tmp_off, const uint32_t* __restrict__ pre,
           const uint32_t* __restrict__ totinv, uint4* __restrict__ st_out, uint32_t* __restrict__ keys_out,
-          uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets) {
+          uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets, int B) {
   using P = typename C::Fp;
   constexpr int PW = (2 * P::L) / 4, FW = P::L / 4, NW = 2 * PW + FW;
   extern __shared__ uint4 aff_stage[];   // [2][NW][AFF_THREADS]
-  const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * AFF_B);
+  const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * B);
   Fe<P> r = ld_fe<P>(totinv + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L);
   // fetch(j): read the two blocks of merge j and start the copies of its operands
   auto fetch = [&](int j, int buf, AffPair& a, uint32_t& seg, uint32_t& i) -> bool {
@@ -190,10 +191,10 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
   };
   AffPair a, an;
   uint32_t seg = 0, i = 0, segn = 0, in_ = 0;
-  bool have = fetch(AFF_B - 1, (AFF_B - 1) & 1, a, seg, i);
+  bool have = fetch(B - 1, (B - 1) & 1, a, seg, i);
   asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll 1
-  for (int j = AFF_B - 1; j >= 0; j--) {
+  for (int j = B - 1; j >= 0; j--) {
     const bool have_next = fetch(j - 1, (j - 1) & 1, an, segn, in_);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -520,32 +521,26 @@ void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t*
 
 // ---- host driver: R levels over sorted pairs, then the records ------------------------------------------------------
 template <class C>
-int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int nseg,
-                       int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w, const AffStreams& as,
-                       int chunk_rec, uint32_t cps, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
+int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int R,
+                       uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w, int chunk_rec, uint32_t cps,
+                       XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
   using P = typename C::Fp;
   int launches = 0;
   int inl = -1;   // code shape of the additions: multiplications inlined (1) or out of line (0); $ZKB200_AFF_INLINE
   if (inl < 0) { const char* e = getenv("ZKB200_AFF_INLINE"); inl = e ? atoi(e) : (P::L > 8 ? 0 : 1); }
   const size_t smem = aff_stage_bytes<P>();
-  const int G = (as.groups == 2 && nseg >= 2) ? 2 : 1;
-  cudaStream_t big[2] = {s, s}, chain[2] = {s, s};
-  int seg0[2] = {0, 0}, segs[2] = {nseg, 0};
-  size_t tmp_base[2] = {0, 0}, binv_base[2] = {0, 0};
-  if (G == 2) {
-    cudaEventRecord(as.ev_start, s);
-    for (int g = 0; g < 2; g++) {
-      big[g] = as.big[g];
-      chain[g] = as.chain[g];
-      int s1;
-      aff_group_range(nseg, 2, g, seg0[g], s1);
-      segs[g] = s1 - seg0[g];
-      cudaStreamWaitEvent(big[g], as.ev_start, 0);
-    }
-    AffSizes z0 = aff_sizes(n, segs[0], R);
-    tmp_base[1] = z0.tmp_points;
-    binv_base[1] = z0.binv_elems + 64;
+  const int G = ln.n;
+  const cudaStream_t* big = ln.big;
+  const cudaStream_t* chain = ln.chain;
+  const int* seg0 = ln.seg0;
+  const int* segs = ln.segs;
+  size_t tmp_per_seg = 0;
+  {
+    size_t nin = n;
+    for (int r = 0; r < R; r++) { nin = (nin + 1) / 2; tmp_per_seg += nin; }
   }
+  const size_t tmp_base[2] = {(size_t)seg0[0] * tmp_per_seg, (size_t)seg0[1] * tmp_per_seg};
+  const size_t binv_base[2] = {0, ln.binv_stride};
   // per level: blocks per segment going in, merges per segment
   uint32_t nin_l[16], nm_l[16];
   {
@@ -553,28 +548,38 @@ int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* val
     for (int r = 0; r < R; r++) { nin_l[r] = nin; nm_l[r] = (nin + 1) / 2; nin = nm_l[r]; }
   }
   size_t lvl_off[2] = {tmp_base[0], tmp_base[1]};   // where the current level's sums start in the temporary array
+  // merges per thread: AFF_B (measured: fewer merges per thread = more threads = more inversion-chain work, a loss
+  // even for small levels); $ZKB200_AFF_B overrides, down to AFF_B_MIN
+  static int forced_B = -1;
+  if (forced_B < 0) { const char* e = getenv("ZKB200_AFF_B"); forced_B = e ? atoi(e) : 0; }
+  auto pick_B = [&](uint32_t) -> int {
+    if (forced_B > 0) return forced_B > AFF_B ? AFF_B : (forced_B < AFF_B_MIN ? AFF_B_MIN : forced_B);
+    return AFF_B;
+  };
   uint32_t* inv[2] = {nullptr, nullptr};
   // step 1 + 2 of level r for group g: running products on the group's stream, inversion chain on its chain stream
   auto do_prod = [&](int g, int r) {
     const uint32_t nin = nin_l[r], nm = nm_l[r], total = (uint32_t)segs[g] * nm;
-    const unsigned blocks = (total + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
+    const int B = pick_B(total);
+    const unsigned blocks = (total + AFF_THREADS * B - 1) / (AFF_THREADS * B);
     const uint32_t* kg = keys + (size_t)seg0[g] * n;
     const uint32_t* vg = vals + (size_t)seg0[g] * n;
     const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * nin;
     uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
     uint32_t* tot = w.binv + binv_base[g] * P::L;
     const size_t T0 = (size_t)blocks * AFF_THREADS;
-    if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot);
-    else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot);
+    if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot, B);
+    else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot, B);
     launches++;
-    if (G == 2) { cudaEventRecord(as.ev_a[g], big[g]); cudaStreamWaitEvent(chain[g], as.ev_a[g], 0); }
+    if (big[g] != chain[g]) { cudaEventRecord(ln.ev_a[g], big[g]); cudaStreamWaitEvent(chain[g], ln.ev_a[g], 0); }
     launches += batch_invert<P>(chain[g], tot, T0, tot + T0 * P::L, &inv[g]);
-    if (G == 2) { cudaEventRecord(as.ev_c[g], chain[g]); cudaStreamWaitEvent(big[g], as.ev_c[g], 0); }
+    if (big[g] != chain[g]) { cudaEventRecord(ln.ev_c[g], chain[g]); cudaStreamWaitEvent(big[g], ln.ev_c[g], 0); }
   };
   // step 3 of level r for group g
   auto do_add = [&](int g, int r) {
     const uint32_t nin = nin_l[r], nm = nm_l[r], total = (uint32_t)segs[g] * nm;
-    const unsigned blocks = (total + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
+    const int B = pick_B(total);
+    const unsigned blocks = (total + AFF_THREADS * B - 1) / (AFF_THREADS * B);
     const bool last = r == R - 1;
     const uint32_t* kg = keys + (size_t)seg0[g] * n;
     const uint32_t* vg = vals + (size_t)seg0[g] * n;
@@ -590,11 +595,11 @@ int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* val
     if (inl) {                                                                                                                \
       cudaFuncSetAttribute(k_aff_add<C, L0, LA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       k_aff_add<C, L0, LA, false><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off, \
-                                                                         pre, inv[g], st_out, ko, vo, NB, bg);                \
+                                                                         pre, inv[g], st_out, ko, vo, NB, bg, B);             \
     } else {                                                                                                                  \
       cudaFuncSetAttribute(k_aff_add<C, L0, LA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
       k_aff_add<C, L0, LA, true><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off,  \
-                                                                        pre, inv[g], st_out, ko, vo, NB, bg);                 \
+                                                                        pre, inv[g], st_out, ko, vo, NB, bg, B);              \
     }                                                                                                                         \
   } while (0)
     if (r == 0 && last) ZK_AFF_ADD(true, true);
@@ -611,7 +616,6 @@ int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* val
                              segs[g], chunk_rec, cps, NB, buckets + (size_t)seg0[g] * NB, heads + (size_t)seg0[g] * cps,
                              head_keys + (size_t)seg0[g] * cps);
     launches++;
-    if (G == 2) { cudaEventRecord(as.ev_done[g], big[g]); cudaStreamWaitEvent(s, as.ev_done[g], 0); }
   };
   // Enqueue order = execution order of the big kernels (equal-priority streams drain first come first served):
   // a group's next running products follow its additions immediately, so that its inversion chain runs under the
@@ -628,9 +632,9 @@ int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* val
 }
 
 #define ZK_INSTANTIATE_AFF(C)                                                                                             \
-  template int launch_affine_tree<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,   \
-                                     uint32_t, XyzzMem<C::Fp>*, const AffWork&, const AffStreams&, int, uint32_t,         \
-                                     XyzzMem<C::Fp>*, uint32_t*);                                                         \
+  template int launch_affine_tree<C>(const AffLanes&, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int,     \
+                                     uint32_t, XyzzMem<C::Fp>*, const AffWork&, int, uint32_t, XyzzMem<C::Fp>*,           \
+                                     uint32_t*);                                                                          \
   template void launch_accumulate_rec<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, \
                                          size_t, int, int, uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);
 

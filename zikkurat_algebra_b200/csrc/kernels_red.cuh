@@ -157,6 +157,27 @@ k_tail(const XyzzMem<typename C::Fp>* __restrict__ Rw, int nmsm, int W, int c, i
   if (tm.t == 0) write_result<P>(out + (size_t)m * (4 * P::L), acc, mode);
 }
 
+// Horner over the Wg window sums of ONE group of consecutive windows (top window first), then `extra` more
+// doublings = c * (index of the group's lowest window): the group's share of the result, stored as XYZZ.
+// Lets the combination of the upper windows run while the lower windows are still being accumulated.
+template <class C>
+__global__ void k_tail_group(const XyzzMem<typename C::Fp>* __restrict__ Rw, int Wg, int c, int extra,
+                             XyzzMem<typename C::Fp>* __restrict__ out) {
+  using P = typename C::Fp;
+  if (blockIdx.x != 0 || threadIdx.x >= 4) return;
+  Team tm;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int w = Wg - 1; w >= 0; w--) {
+    const int nd = w == Wg - 1 ? 0 : c;
+#pragma unroll 1
+    for (int d = 0; d < nd; d++) acc = xyzz_dbl_team<P>(tm, acc);
+    xyzz_add_tm<P>(tm, acc, load_xyzz<P>(Rw + w));
+  }
+#pragma unroll 1
+  for (int d = 0; d < extra; d++) acc = xyzz_dbl_team<P>(tm, acc);
+  if (tm.t == 0) store_xyzz<P>(out, acc);
+}
+
 // sum of k group elements given in one of the reference's representations (multi-GPU combine, K8)
 //   in_mode: OUT_PROJ / OUT_JAC / OUT_XYZZ (records of 3L / 3L / 4L words)
 template <class C>
@@ -301,6 +322,10 @@ void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, in
   k_tail<C><<<(nmsm * 4 + 31) / 32, 32, 0, s>>>(Rw, nmsm, W, c, mode, out);
 }
 template <class C>
+void launch_tail_group(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int Wg, int c, int extra, XyzzMem<typename C::Fp>* out) {
+  k_tail_group<C><<<1, 32, 0, s>>>(Rw, Wg, c, extra, out);
+}
+template <class C>
 void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out) {
   k_sum_points<C><<<1, 32, 0, s>>>(in, k, in_mode, out_mode, out);
 }
@@ -312,6 +337,7 @@ void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, i
                                       XyzzMem<C::Fp>*, XyzzMem<C::Fp>*);                                                   \
   template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*);                        \
   template void launch_sum_points<C>(cudaStream_t, const uint32_t*, int, int, int, uint32_t*);                             \
+  template void launch_tail_group<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, XyzzMem<C::Fp>*);                 \
   template void launch_gen_chain<C>(cudaStream_t, const uint32_t*, unsigned long long, size_t, uint32_t*);               \
   template void launch_batch_to_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);                         \
   template void launch_batch_from_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);

@@ -83,7 +83,8 @@ template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, 
 template <class C> int accumulate_resident_threads();
 
 // ---- affine pre-reduction tree (kernels_aff.cuh) ----
-constexpr int AFF_B = 16;         // merges per thread and level
+constexpr int AFF_B = 16;         // merges per thread and level (at most; small levels use fewer, down to AFF_B_MIN)
+constexpr int AFF_B_MIN = 4;
 constexpr int AFF_THREADS = 128;
 constexpr int BINV_G = 4;         // elements per thread in the product trees of the batch inversion
 struct AffWork {          // device workspaces, sized by aff_sizes()
@@ -127,7 +128,7 @@ inline AffSizes aff_sizes(size_t n, int nseg, int R) {
     z.tmp_points += (size_t)nseg * nm;
     if (r == 0) {
       z.pre_elems = (size_t)nseg * nm;
-      size_t blocks = ((size_t)nseg * nm + AFF_THREADS * AFF_B - 1) / (AFF_THREADS * AFF_B);
+      size_t blocks = ((size_t)nseg * nm + AFF_THREADS * AFF_B_MIN - 1) / (AFF_THREADS * AFF_B_MIN);   // most threads
       z.binv_elems = blocks * AFF_THREADS + binv_workspace_elems(blocks * AFF_THREADS) + 64;
       z.st0 = (size_t)nseg * nm;
     }
@@ -138,33 +139,26 @@ inline AffSizes aff_sizes(size_t n, int nseg, int R) {
   z.rec = (size_t)nseg * z.nrec;
   return z;
 }
-// Optional second lane for the tree: the segments are cut into `groups` groups that run on their own streams, the
-// latency-bound inversion chains on high-priority streams, so that one group's chain runs under the other group's
-// additions instead of leaving the GPU idle.  groups = 1: everything on the caller's stream.
-struct AffStreams {
-  int groups;
+// Lanes of the tree: one or two ranges of segments that run on their own streams, the latency-bound inversion
+// chains on high-priority streams, so that one lane's chain runs under the other lane's additions instead of leaving
+// the GPU idle.  The caller orders the lane streams against its own stream (events before and after).
+struct AffLanes {
+  int n;                       // 1 or 2
+  int seg0[2], segs[2];        // segment range of each lane
   cudaStream_t big[2], chain[2];
-  cudaEvent_t ev_a[2], ev_c[2], ev_done[2], ev_start;
+  cudaEvent_t ev_a[2], ev_c[2];
+  size_t binv_stride;          // elements between the two lanes' inversion workspaces
 };
 inline void aff_group_range(int nseg, int groups, int g, int& s0, int& s1) {
   s0 = (int)((long long)nseg * g / groups);
   s1 = (int)((long long)nseg * (g + 1) / groups);
 }
-inline size_t aff_binv_elems_total(size_t n, int nseg, int R, int groups) {
-  size_t tot = 0;
-  for (int g = 0; g < groups; g++) {
-    int s0, s1;
-    aff_group_range(nseg, groups, g, s0, s1);
-    tot += aff_sizes(n, s1 - s0, R).binv_elems + 64;
-  }
-  return tot;
-}
-// R levels of pairwise affine sums over the sorted pairs, then the XYZZ accumulation of the surviving records
-// (chunk_rec record slots per thread, cps threads per segment; heads / head_keys as for launch_accumulate).
-template <class C> int launch_affine_tree(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n,
-                                          int nseg, int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w,
-                                          const AffStreams& as, int chunk_rec, uint32_t cps, XyzzMem<typename C::Fp>* heads,
-                                          uint32_t* head_keys);
+// R levels of pairwise affine sums over the sorted pairs of the lanes' segments, then the XYZZ accumulation of the
+// surviving records (chunk_rec record slots per thread, cps threads per segment; heads / head_keys indexed by segment
+// as for launch_accumulate).  keys / vals / buckets / heads are the arrays of ALL segments.
+template <class C> int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
+                                          size_t n, int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w,
+                                          int chunk_rec, uint32_t cps, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys);
 template <class C> void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
                                               const uint32_t* tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
                                               uint32_t NB, XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads,
@@ -178,6 +172,8 @@ template <class C> void launch_reduce_next(cudaStream_t s, const XyzzMem<typenam
                                            size_t total_out, int log_m, int log_M, XyzzMem<typename C::Fp>* Uout,
                                            XyzzMem<typename C::Fp>* Vout);
 template <class C> void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out);
+template <class C> void launch_tail_group(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int Wg, int c, int extra,
+                                          XyzzMem<typename C::Fp>* out);
 template <class C> void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out);
 template <class C> void launch_batch_to_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);
 template <class C> void launch_batch_from_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);

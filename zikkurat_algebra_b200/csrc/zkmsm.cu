@@ -37,7 +37,7 @@ namespace {
 enum Buf {
   B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
   B_U0, B_V0, B_U1, B_V1, B_OUT, B_NTT_TABLE, B_AFF_TMP, B_AFF_PRE, B_AFF_BINV, B_AFF_ST0, B_AFF_ST1, B_AFF_KEYS,
-  B_AFF_VALS, B_COUNT
+  B_AFF_VALS, B_PARTIALS, B_COUNT
 };
 constexpr int N_EV = 9;
 constexpr int MAX_DEV = 16;
@@ -55,7 +55,13 @@ struct DeviceCtx {
   std::atomic<bool> ready{false};
   int dev = 0;
   cudaStream_t s_main = nullptr, s_copy = nullptr;
-  AffStreams aff{};           // second lane of the affine pre-reduction (kernels_aff.cuh)
+  struct Pipeline {           // lanes and post-processing streams of the window-group pipeline (run_msm)
+    cudaStream_t s_big[2] = {nullptr, nullptr}, s_chain[2] = {nullptr, nullptr};
+    cudaStream_t big[2] = {nullptr, nullptr}, chain[2] = {nullptr, nullptr};   // the ones in use for the current call
+    cudaStream_t post[8] = {nullptr};
+    cudaEvent_t ev_a[2] = {nullptr}, ev_c[2] = {nullptr}, ev_lane[2] = {nullptr}, ev_sorted = nullptr;
+    cudaEvent_t ev_fix[8] = {nullptr}, ev_post[8] = {nullptr};
+  } pl;
   cudaEvent_t ev[N_EV + 1] = {nullptr};
   cudaEvent_t gev[6 * 8] = {nullptr};  // per input slice: accumulate start/end, fix-up end, recode start, sort end, recode end
   cudaEvent_t ev_sc[8] = {nullptr}, ev_pt[8] = {nullptr};   // per input slice: scalars / points have arrived
@@ -129,15 +135,19 @@ DeviceCtx& get_ctx(int d = -1) {
       {
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-        cx.aff.groups = 2;
         for (int g = 0; g < 2; g++) {
-          CK(cudaStreamCreateWithPriority(&cx.aff.big[g], cudaStreamNonBlocking, lo_pri));
-          CK(cudaStreamCreateWithPriority(&cx.aff.chain[g], cudaStreamNonBlocking, hi_pri));
-          CK(cudaEventCreateWithFlags(&cx.aff.ev_a[g], cudaEventDisableTiming));
-          CK(cudaEventCreateWithFlags(&cx.aff.ev_c[g], cudaEventDisableTiming));
-          CK(cudaEventCreateWithFlags(&cx.aff.ev_done[g], cudaEventDisableTiming));
+          CK(cudaStreamCreateWithPriority(&cx.pl.s_big[g], cudaStreamNonBlocking, lo_pri));
+          CK(cudaStreamCreateWithPriority(&cx.pl.s_chain[g], cudaStreamNonBlocking, hi_pri));
+          CK(cudaEventCreateWithFlags(&cx.pl.ev_a[g], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&cx.pl.ev_c[g], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&cx.pl.ev_lane[g], cudaEventDisableTiming));
         }
-        CK(cudaEventCreateWithFlags(&cx.aff.ev_start, cudaEventDisableTiming));
+        for (int g = 0; g < 8; g++) {
+          CK(cudaStreamCreateWithPriority(&cx.pl.post[g], cudaStreamNonBlocking, hi_pri));
+          CK(cudaEventCreateWithFlags(&cx.pl.ev_fix[g], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&cx.pl.ev_post[g], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&cx.pl.ev_sorted, cudaEventDisableTiming));
       }
       for (int i = 0; i < 6 * 8; i++) CK(cudaEventCreate(&cx.gev[i]));
       for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
@@ -331,22 +341,6 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // Sorted pairs per thread: every accumulate grid is a whole number of waves of resident threads so that
     // all SMs drain together; about 48 insertions per thread for small problems (several waves), up to 192
     // for big ones (fewer chunk heads to fold afterwards, still >= 12 waves).
-    auto pick_chunk = [&](size_t pairs_total, size_t per_seg) -> int {
-      const char* e = getenv("ZKB200_CHUNK");
-      if (e && atoi(e) > 0) return atoi(e);
-      double target = (double)pairs_total / ((double)resident * 12.0);
-      if (target < 48.0) target = 48.0;
-      if (target > 192.0) target = 192.0;
-      double waves = (double)pairs_total / ((double)resident * target);
-      size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
-      size_t per_seg_threads = ((size_t)resident * nw) / (size_t)nseg;  // threads available to one segment
-      if (per_seg_threads < 1) per_seg_threads = 1;
-      size_t ch = (per_seg + per_seg_threads - 1) / per_seg_threads;
-      if (ch < 8) ch = 8;
-      if (ch > 1024) ch = 1024;
-      return (int)ch;
-    };
-    const int chunk = pick_chunk(pairs_max, nmax);
     // ---- affine pre-reduction (kernels_aff.cuh): R levels of pairwise affine sums in front of k_accumulate ----
     int R = 0;
     if constexpr (HasAffineTree<C>::value) {
@@ -372,24 +366,58 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       }
     }
     st.aff_levels = R;
-    AffSizes az{};
-    AffWork aw{};
-    AffStreams as = cx.aff;
+    // ---- window groups and lanes (see the slice loop) ----
+    // split_tail: a single MSM's windows are cut into NG groups, top windows first; a group's bucket reduction and
+    // its share of the window combination start as soon as its buckets are complete, under the accumulation of the
+    // lower groups.  Two lanes (streams) work on two groups at a time so that the latency-bound kernels of one lane
+    // (inversion chains of the affine tree) run under the other lane's additions.
+    int NG = 1;
+    if (nmsm == 1 && W >= 8) {
+      const char* e = getenv("ZKB200_WGROUPS");
+      NG = e ? atoi(e) : 2;   // measured: 2 groups -1.3 % (BLS12-381 2^20) .. -2 % (2^22); 4 and 8 lose (smaller kernels)
+      if (NG < 1) NG = 1;
+      if (NG > 8) NG = 8;
+    }
+    const bool split_tail = NG > 1;
+    int nlanes = 1;
     {
       const char* e = getenv("ZKB200_AFF_GROUPS");
-      as.groups = (e ? atoi(e) : 2) == 2 ? 2 : 1;
+      if ((e ? atoi(e) : 2) == 2 && nseg >= 2 && (R > 0 || split_tail)) nlanes = 2;
     }
+    if (!split_tail) NG = nlanes;   // without the split the lanes simply halve the segments
+    const int conc_segs = (nseg + NG - 1) / NG * nlanes;   // segments in flight at a time
+    auto pick_chunk = [&](size_t per_seg) -> int {
+      const char* e = getenv("ZKB200_CHUNK");
+      if (e && atoi(e) > 0) return atoi(e);
+      const size_t pairs_total = per_seg * (size_t)conc_segs;
+      double target = (double)pairs_total / ((double)resident * 12.0);
+      if (target < 48.0) target = 48.0;
+      if (target > 192.0) target = 192.0;
+      double waves = (double)pairs_total / ((double)resident * target);
+      size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
+      size_t per_seg_threads = ((size_t)resident * nw) / (size_t)conc_segs;  // threads available to one segment
+      if (per_seg_threads < 1) per_seg_threads = 1;
+      size_t ch = (per_seg + per_seg_threads - 1) / per_seg_threads;
+      if (ch < 8) ch = 8;
+      if (ch > 1024) ch = 1024;
+      return (int)ch;
+    };
+    const int chunk = pick_chunk(nmax);
+    AffSizes az{};
+    AffWork aw{};
     int chunk_rec = chunk;
+    size_t binv_stride = 0;
     if (R > 0) {
       az = aff_sizes(nmax, nseg, R);
+      binv_stride = az.binv_elems + 64;
       aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)(2 * L) * 4);
       aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, az.pre_elems * (size_t)L * 4);
-      aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, (aff_binv_elems_total(nmax, nseg, R, 2) + az.binv_elems) * (size_t)L * 4);
+      aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, 2 * binv_stride * (size_t)L * 4);
       aw.st[0] = (uint4*)cx.ensure(B_AFF_ST0, az.st0 * 16 + 16);
       aw.st[1] = (uint4*)cx.ensure(B_AFF_ST1, az.st1 * 16 + 16);
       aw.keys_out = (uint32_t*)cx.ensure(B_AFF_KEYS, az.rec * 4 + 16);
       aw.vals_out = (uint32_t*)cx.ensure(B_AFF_VALS, az.rec * 4 + 16);
-      chunk_rec = pick_chunk(az.rec, az.nrec);
+      chunk_rec = pick_chunk(az.nrec);
     }
     uint32_t cps_max = (uint32_t)((nmax + chunk - 1) / chunk);
     if (R > 0) {
@@ -398,9 +426,24 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     }
     Mem* heads = (Mem*)cx.ensure(B_HEADS, (size_t)nseg * cps_max * sizeof(Mem));
     uint32_t* head_keys = (uint32_t*)cx.ensure(B_HEADKEYS, (size_t)nseg * cps_max * 4);
-    const size_t cap2 = (size_t)nseg * ((cps_max + FIXUP_FAN - 1) / FIXUP_FAN);
-    Mem* heads2 = (Mem*)cx.ensure(B_HEADS2, cap2 * sizeof(Mem));
-    uint32_t* head_keys2 = (uint32_t*)cx.ensure(B_HEADKEYS2, cap2 * 4);
+    const size_t cap2_per_seg = (cps_max + FIXUP_FAN - 1) / FIXUP_FAN;
+    Mem* heads2 = (Mem*)cx.ensure(B_HEADS2, (size_t)nseg * cap2_per_seg * sizeof(Mem));
+    uint32_t* head_keys2 = (uint32_t*)cx.ensure(B_HEADKEYS2, (size_t)nseg * cap2_per_seg * 4);
+    int log_m1 = 0;
+    if (c - 1 > 0) {
+      const char* e = getenv("ZKB200_LOGM1");
+      log_m1 = e ? atoi(e) : ilog2_floor(((size_t)nseg << (c - 1)) / 32768 + 1);   // about one wave of threads (measured)
+      if (log_m1 < 1) log_m1 = 1;
+      if (log_m1 > 5) log_m1 = 5;
+      if (log_m1 > c - 1) log_m1 = c - 1;
+    }
+    const size_t red_out = (size_t)nseg << (c - 1 - log_m1);
+    Mem* Ub[2] = {(Mem*)cx.ensure(B_U0, red_out * sizeof(Mem)), (Mem*)cx.ensure(B_U1, red_out * sizeof(Mem))};
+    Mem* Vb[2] = {(Mem*)cx.ensure(B_V0, red_out * sizeof(Mem)), (Mem*)cx.ensure(B_V1, red_out * sizeof(Mem))};
+    Mem* partials = (Mem*)cx.ensure(B_PARTIALS, 16 * sizeof(Mem));
+    if (nlanes == 1) { cx.pl.big[0] = s; cx.pl.chain[0] = s; } else { cx.pl.big[0] = cx.pl.s_big[0]; cx.pl.chain[0] = cx.pl.s_chain[0]; }
+    cx.pl.big[1] = cx.pl.s_big[1];
+    cx.pl.chain[1] = cx.pl.s_chain[1];
 
     for (int k = 0; k < K; k++) {
       const size_t nk = lo[k + 1] - lo[k];
@@ -438,75 +481,130 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       CK(cudaEventRecord(ge[0], s));
       Mem* kb_ = buckets + (size_t)k * slice_stride;
       const uint32_t* pts_k = d_points + lo[k] * (size_t)(2 * L);
-      uint32_t cps = 0;
-      if constexpr (HasAffineTree<C>::value) {
-        if (R > 0) {
-          AffSizes zk_ = aff_sizes(nk, nseg, R);
-          cps = (uint32_t)((zk_.nrec + chunk_rec - 1) / chunk_rec);
-          g_launches += launch_affine_tree<C>(s, keys[cur], vals[cur], pts_k, nk, nseg, R, NB, kb_, aw, as, chunk_rec, cps, heads,
-                                              head_keys);
+      AffSizes zk_ = aff_sizes(nk, nseg, R > 0 ? R : 1);
+      const uint32_t cps = R > 0 ? (uint32_t)((zk_.nrec + chunk_rec - 1) / chunk_rec) : (uint32_t)((nk + chunk - 1) / chunk);
+      const bool last_slice = k == K - 1;
+      // Window groups, top windows first, two at a time on the two lanes.  A group's fix-up runs on its lane; after
+      // the LAST slice its bucket reduction and its share of the window combination follow on a high-priority stream
+      // of their own, under the accumulation of the lower groups.
+      CK(cudaEventRecord(cx.pl.ev_sorted, s));
+      for (int l = 0; l < nlanes; l++) CK(cudaStreamWaitEvent(cx.pl.big[l], cx.pl.ev_sorted, 0));
+      for (int g = NG - 1; g >= 0; g -= nlanes) {
+        AffLanes ln{};
+        ln.n = (g - 1 >= 0 && nlanes == 2) ? 2 : 1;
+        ln.binv_stride = binv_stride;
+        int gl[2] = {g, g - 1};
+        for (int l = 0; l < ln.n; l++) {
+          int s1;
+          aff_group_range(nseg, NG, gl[l], ln.seg0[l], s1);
+          ln.segs[l] = s1 - ln.seg0[l];
+          ln.big[l] = cx.pl.big[l];
+          ln.chain[l] = cx.pl.chain[l];
+          ln.ev_a[l] = cx.pl.ev_a[l];
+          ln.ev_c[l] = cx.pl.ev_c[l];
         }
-      }
-      if (R == 0) {
-        cps = (uint32_t)((nk + chunk - 1) / chunk);
-        g_launches++;
-        launch_accumulate<C>(s, keys[cur], vals[cur], pts_k, nk, nseg, chunk, cps, NB, kb_, heads, head_keys);
-      }
-      CK(cudaGetLastError());
-      CK(cudaEventRecord(ge[1], s));
-      {  // fold the chunk heads into the buckets: log_FAN(chunks) small levels
-        uint32_t T = cps;
-        Mem* hb[2] = {heads, heads2};
-        uint32_t* kb[2] = {head_keys, head_keys2};
-        int src = 0;
-        for (;;) {
-          uint32_t T_out = (T + FIXUP_FAN - 1) / FIXUP_FAN;
-          int last = T_out == 1;
-          g_launches++;
-          launch_fixup_level<C>(s, kb[src], hb[src], T, kb[src ^ 1], hb[src ^ 1], T_out, nseg, NB, kb_, last);
+        if constexpr (HasAffineTree<C>::value) {
+          if (R > 0)
+            g_launches += launch_affine_tree<C>(ln, keys[cur], vals[cur], pts_k, nk, R, NB, kb_, aw, chunk_rec, cps, heads, head_keys);
+        }
+        for (int l = 0; l < ln.n; l++) {
+          const int s0 = ln.seg0[l], ns = ln.segs[l];
+          cudaStream_t sl = ln.big[l];
+          if (R == 0) {
+            g_launches++;
+            launch_accumulate<C>(sl, keys[cur] + (size_t)s0 * nk, vals[cur] + (size_t)s0 * nk, pts_k, nk, ns, chunk, cps, NB,
+                                 kb_ + (size_t)s0 * NB, heads + (size_t)s0 * cps, head_keys + (size_t)s0 * cps);
+          }
           CK(cudaGetLastError());
-          if (last) break;
-          T = T_out;
-          src ^= 1;
+          {  // fold the chunk heads into the buckets: log_FAN(chunks) small levels
+            uint32_t T = cps;
+            Mem* hb[2] = {heads + (size_t)s0 * cps, heads2 + (size_t)s0 * cap2_per_seg};
+            uint32_t* kb[2] = {head_keys + (size_t)s0 * cps, head_keys2 + (size_t)s0 * cap2_per_seg};
+            int src = 0;
+            for (;;) {
+              uint32_t T_out = (T + FIXUP_FAN - 1) / FIXUP_FAN;
+              int last = T_out == 1;
+              g_launches++;
+              launch_fixup_level<C>(sl, kb[src], hb[src], T, kb[src ^ 1], hb[src ^ 1], T_out, ns, NB, kb_ + (size_t)s0 * NB, last);
+              CK(cudaGetLastError());
+              if (last) break;
+              T = T_out;
+              src ^= 1;
+            }
+          }
+          if (last_slice && split_tail) {
+            // ---- this group's bucket reduction by levels + its share of the window combination ----
+            cudaStream_t sp = cx.pl.post[gl[l]];
+            CK(cudaEventRecord(cx.pl.ev_fix[gl[l]], sl));
+            CK(cudaStreamWaitEvent(sp, cx.pl.ev_fix[gl[l]], 0));
+            const size_t ubase = (size_t)s0 << (c - 1 - log_m1);
+            int logS = c - 1;
+            size_t total_out = (size_t)ns << (logS - log_m1);
+            g_launches++;
+            launch_reduce_first<C>(sp, buckets + (size_t)s0 * NB, K, slice_stride, total_out, log_m1, Ub[0] + ubase, Vb[0] + ubase);
+            CK(cudaGetLastError());
+            logS -= log_m1;
+            int log_M = log_m1, lv = 0;
+            while (logS > 0) {
+              int lm = logS > 3 ? 3 : logS;
+              total_out = (size_t)ns << (logS - lm);
+              g_launches++;
+              launch_reduce_next<C>(sp, Ub[lv] + ubase, Vb[lv] + ubase, total_out, lm, log_M, Ub[lv ^ 1] + ubase, Vb[lv ^ 1] + ubase);
+              CK(cudaGetLastError());
+              logS -= lm;
+              log_M += lm;
+              lv ^= 1;
+            }
+            g_launches++;
+            launch_tail_group<C>(sp, Ub[lv] + ubase, ns, c, c * s0, partials + gl[l]);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(cx.pl.ev_post[gl[l]], sp));
+          }
         }
       }
+      // the caller's stream resumes when the lanes are done (the next slice re-uses the pair arrays)
+      for (int l = 0; l < nlanes; l++) {
+        if (cx.pl.big[l] == s) continue;
+        CK(cudaEventRecord(cx.pl.ev_lane[l], cx.pl.big[l]));
+        CK(cudaStreamWaitEvent(s, cx.pl.ev_lane[l], 0));
+      }
+      CK(cudaEventRecord(ge[1], s));
       CK(cudaEventRecord(ge[2], s));
     }
 
-    // ---- bucket reduction by levels ----
     CK(cudaEventRecord(cx.ev[5], s));
-    int log_m1 = 0;
-    if (c - 1 > 0) {
-      const char* e = getenv("ZKB200_LOGM1");
-      log_m1 = e ? atoi(e) : ilog2_floor(((size_t)nseg << (c - 1)) / 32768 + 1);   // about one wave of threads (measured)
-      if (log_m1 < 1) log_m1 = 1;
-      if (log_m1 > 5) log_m1 = 5;
-      if (log_m1 > c - 1) log_m1 = c - 1;
-    }
-    int logS = c - 1;
-    size_t total_out = (size_t)nseg << (logS - log_m1);
-    Mem* Ub[2] = {(Mem*)cx.ensure(B_U0, total_out * sizeof(Mem)), (Mem*)cx.ensure(B_U1, (total_out / 2 + 1) * sizeof(Mem))};
-    Mem* Vb[2] = {(Mem*)cx.ensure(B_V0, total_out * sizeof(Mem)), (Mem*)cx.ensure(B_V1, (total_out / 2 + 1) * sizeof(Mem))};
-    g_launches++;
-    launch_reduce_first<C>(s, buckets, K, slice_stride, total_out, log_m1, Ub[0], Vb[0]);
-    CK(cudaGetLastError());
-    logS -= log_m1;
-    int log_M = log_m1, lv = 0;
-    while (logS > 0) {
-      int lm = logS > 3 ? 3 : logS;
-      total_out = (size_t)nseg << (logS - lm);
+    if (split_tail) {
+      // ---- the groups' shares are summed and converted to the output representation ----
+      for (int g = 0; g < NG; g++) CK(cudaStreamWaitEvent(s, cx.pl.ev_post[g], 0));
+      CK(cudaEventRecord(cx.ev[6], s));
       g_launches++;
-      launch_reduce_next<C>(s, Ub[lv], Vb[lv], total_out, lm, log_M, Ub[lv ^ 1], Vb[lv ^ 1]);
+      launch_sum_points<C>(s, (const uint32_t*)partials, NG, OUT_XYZZ, out_mode, d_out);
       CK(cudaGetLastError());
-      logS -= lm;
-      log_M += lm;
-      lv ^= 1;
+    } else {
+      // ---- bucket reduction by levels ----
+      int logS = c - 1;
+      size_t total_out = (size_t)nseg << (logS - log_m1);
+      g_launches++;
+      launch_reduce_first<C>(s, buckets, K, slice_stride, total_out, log_m1, Ub[0], Vb[0]);
+      CK(cudaGetLastError());
+      logS -= log_m1;
+      int log_M = log_m1, lv = 0;
+      while (logS > 0) {
+        int lm = logS > 3 ? 3 : logS;
+        total_out = (size_t)nseg << (logS - lm);
+        g_launches++;
+        launch_reduce_next<C>(s, Ub[lv], Vb[lv], total_out, lm, log_M, Ub[lv ^ 1], Vb[lv ^ 1]);
+        CK(cudaGetLastError());
+        logS -= lm;
+        log_M += lm;
+        lv ^= 1;
+      }
+      CK(cudaEventRecord(cx.ev[6], s));
+      // ---- window combination (Horner) + output conversion ----
+      g_launches++;
+      launch_tail<C>(s, Ub[lv], nmsm, W, c, out_mode, d_out);
+      CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(cx.ev[6], s));
-    // ---- window combination (Horner) + output conversion ----
-    g_launches++;
-    launch_tail<C>(s, Ub[lv], nmsm, W, c, out_mode, d_out);
-    CK(cudaGetLastError());
     st.have_phases = true;
   }
   CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
