@@ -692,6 +692,15 @@ def test_affine_pre_reduction_levels(zk, curve):
             with _Env(ZKB200_AFFINE=R):
                 got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
             assert got.tobytes() == want, (n, R)
+    # lanes are concurrent streams sharing workspaces: repeat small problems with many windows in every lane mode
+    for mode in (dict(ZKB200_STAGGER=0), dict(ZKB200_STAGGER=3), dict(ZKB200_STAGGER=4), dict(ZKB200_STAGGER=0, ZKB200_WGROUPS=4)):
+        for rep in range(6):
+            n = (64, 100, 257)[rep % 3]
+            pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=300 + rep, reduce=False)
+            want = cpu_affine(curve, sc, pts).tobytes()
+            with _Env(ZKB200_AFFINE=5, **mode):
+                got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
+            assert got.tobytes() == want, (mode, n, rep)
     # window widths: c = 2 gives runs of ~n/2, c = 16 gives almost no equal keys
     n = 3000
     pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=7, reduce=False)

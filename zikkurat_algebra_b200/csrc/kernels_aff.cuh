@@ -540,13 +540,17 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     for (int r = 0; r < R; r++) { nin = (nin + 1) / 2; tmp_per_seg += nin; }
   }
   const size_t tmp_base[2] = {(size_t)seg0[0] * tmp_per_seg, (size_t)seg0[1] * tmp_per_seg};
-  const size_t binv_base[2] = {0, ln.binv_stride};
+  const size_t binv_base[2] = {ln.binv_base0, ln.binv_base0 + ln.binv_stride};
   // per level: blocks per segment going in, merges per segment
   uint32_t nin_l[16], nm_l[16];
   {
     uint32_t nin = (uint32_t)n;
     for (int r = 0; r < R; r++) { nin_l[r] = nin; nm_l[r] = (nin + 1) / 2; nin = nm_l[r]; }
   }
+  // A segment's block states live at a FIXED place of each ping-pong buffer (stride = the widest level that uses
+  // the buffer): lanes are not in lock step, so a level-dependent offset would let one lane's narrow level land in
+  // another lane's wide one.
+  const size_t st_stride[2] = {nm_l[0], R > 1 ? nm_l[1] : 0};
   size_t lvl_off[2] = {tmp_base[0], tmp_base[1]};   // where the current level's sums start in the temporary array
   // merges per thread: AFF_B (measured: fewer merges per thread = more threads = more inversion-chain work, a loss
   // even for small levels); $ZKB200_AFF_B overrides, down to AFF_B_MIN
@@ -564,7 +568,7 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     const unsigned blocks = (total + AFF_THREADS * B - 1) / (AFF_THREADS * B);
     const uint32_t* kg = keys + (size_t)seg0[g] * n;
     const uint32_t* vg = vals + (size_t)seg0[g] * n;
-    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * nin;
+    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * st_stride[(r - 1) & 1];
     uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
     uint32_t* tot = w.binv + binv_base[g] * P::L;
     const size_t T0 = (size_t)blocks * AFF_THREADS;
@@ -583,8 +587,8 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     const bool last = r == R - 1;
     const uint32_t* kg = keys + (size_t)seg0[g] * n;
     const uint32_t* vg = vals + (size_t)seg0[g] * n;
-    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * nin;
-    uint4* st_out = w.st[r & 1] + (size_t)seg0[g] * nm;
+    const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * st_stride[(r - 1) & 1];
+    uint4* st_out = w.st[r & 1] + (size_t)seg0[g] * st_stride[r & 1];
     uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
     uint32_t* ko = w.keys_out + (size_t)seg0[g] * 2 * nm;
     uint32_t* vo = w.vals_out + (size_t)seg0[g] * 2 * nm;

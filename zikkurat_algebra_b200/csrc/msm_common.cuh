@@ -147,6 +147,7 @@ struct AffLanes {
   int seg0[2], segs[2];        // segment range of each lane
   cudaStream_t big[2], chain[2];
   cudaEvent_t ev_a[2], ev_c[2];
+  size_t binv_base0;           // inversion workspace of lane 0 (elements from w.binv)
   size_t binv_stride;          // elements between the two lanes' inversion workspaces
 };
 inline void aff_group_range(int nseg, int groups, int g, int& s0, int& s1) {

@@ -59,6 +59,9 @@ struct DeviceCtx {
     cudaStream_t s_big[2] = {nullptr, nullptr}, s_chain[2] = {nullptr, nullptr};
     cudaStream_t big[2] = {nullptr, nullptr}, chain[2] = {nullptr, nullptr};   // the ones in use for the current call
     cudaStream_t post[8] = {nullptr};
+    cudaStream_t stag_pool[4][4] = {{nullptr}};                        // staggered mode: [lane][priority level] streams
+    cudaStream_t stag_big[4] = {nullptr}, stag_chain[4] = {nullptr};   // the ones in use: lanes of descending priority
+    cudaEvent_t stag_a[4] = {nullptr}, stag_c[4] = {nullptr}, stag_lane[4] = {nullptr};
     cudaEvent_t ev_a[2] = {nullptr}, ev_c[2] = {nullptr}, ev_lane[2] = {nullptr}, ev_sorted = nullptr;
     cudaEvent_t ev_fix[8] = {nullptr}, ev_post[8] = {nullptr};
   } pl;
@@ -148,6 +151,19 @@ DeviceCtx& get_ctx(int d = -1) {
           CK(cudaEventCreateWithFlags(&cx.pl.ev_post[g], cudaEventDisableTiming));
         }
         CK(cudaEventCreateWithFlags(&cx.pl.ev_sorted, cudaEventDisableTiming));
+        for (int g = 0; g < 4; g++) {
+          // lane 0 (top windows) gets the highest of the "big" priorities; chains and post-processing stay above all
+          for (int lv = 0; lv < 4; lv++) {   // level 0 = lowest priority
+            int pri = lo_pri - lv;
+            if (pri < hi_pri + 1) pri = hi_pri + 1 < lo_pri ? hi_pri + 1 : lo_pri;
+            CK(cudaStreamCreateWithPriority(&cx.pl.stag_pool[g][lv], cudaStreamNonBlocking, pri));
+          }
+          cx.pl.stag_big[g] = cx.pl.stag_pool[g][3 - g];
+          CK(cudaStreamCreateWithPriority(&cx.pl.stag_chain[g], cudaStreamNonBlocking, hi_pri));
+          CK(cudaEventCreateWithFlags(&cx.pl.stag_a[g], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&cx.pl.stag_c[g], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&cx.pl.stag_lane[g], cudaEventDisableTiming));
+        }
       }
       for (int i = 0; i < 6 * 8; i++) CK(cudaEventCreate(&cx.gev[i]));
       for (int i = 0; i <= N_EV; i++) CK(cudaEventCreate(&cx.ev[i]));
@@ -378,14 +394,44 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (NG < 1) NG = 1;
       if (NG > 8) NG = 8;
     }
+    // Staggered mode (needs the tree's short-lived blocks): every group gets its own lane, upper windows at higher
+    // stream priority, so the upper groups finish first -- their reduction and their long doubling chains then run
+    // under the lower groups' work -- while each lane's inversion chains hide behind the lower-priority lanes.
+    // Groups from the bottom: [0, W/4), [W/4, W/2), [W/2, W)  ($ZKB200_STAGGER = number of groups 2..4, 0 = off).
+    int stagger = 0;
+    if (nmsm == 1 && W >= 8 && R > 0) {
+      const char* e = getenv("ZKB200_STAGGER");
+      stagger = e ? atoi(e) : 3;
+      if (stagger < 2) stagger = 0;
+      if (stagger > 4) stagger = 4;
+      if (stagger) NG = stagger;
+    }
     const bool split_tail = NG > 1;
     int nlanes = 1;
     {
       const char* e = getenv("ZKB200_AFF_GROUPS");
       if ((e ? atoi(e) : 2) == 2 && nseg >= 2 && (R > 0 || split_tail)) nlanes = 2;
     }
+    if (stagger) {
+      nlanes = 1;
+      // priority level of every lane (lane 0 = top group), one digit each; default: top group above the rest, the
+      // others equal so that they hide each other's inversion chains
+      const char* e = getenv("ZKB200_STAGGER_PRI");
+      const char* dflt = "1000";
+      for (int j = 0; j < 4; j++) {
+        int lv = (e && strlen(e) > (size_t)j ? e[j] : dflt[j]) - '0';
+        if (lv < 0) lv = 0;
+        if (lv > 3) lv = 3;
+        cx.pl.stag_big[j] = cx.pl.stag_pool[j][lv];
+      }
+    }
     if (!split_tail) NG = nlanes;   // without the split the lanes simply halve the segments
-    const int conc_segs = (nseg + NG - 1) / NG * nlanes;   // segments in flight at a time
+    int grp0[9];                    // group g covers segments [grp0[g], grp0[g+1]), bottom windows first
+    for (int g = 0; g <= NG; g++) {
+      if (stagger) grp0[g] = g == 0 ? 0 : (g == NG ? W : (W >> (NG - g)));
+      else grp0[g] = (int)((long long)nseg * g / NG);
+    }
+    const int conc_segs = stagger ? nseg : (nseg + NG - 1) / NG * nlanes;   // segments in flight at a time
     auto pick_chunk = [&](size_t per_seg) -> int {
       const char* e = getenv("ZKB200_CHUNK");
       if (e && atoi(e) > 0) return atoi(e);
@@ -412,7 +458,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       binv_stride = az.binv_elems + 64;
       aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)(2 * L) * 4);
       aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, az.pre_elems * (size_t)L * 4);
-      aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, 2 * binv_stride * (size_t)L * 4);
+      aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, 4 * binv_stride * (size_t)L * 4);
       aw.st[0] = (uint4*)cx.ensure(B_AFF_ST0, az.st0 * 16 + 16);
       aw.st[1] = (uint4*)cx.ensure(B_AFF_ST1, az.st1 * 16 + 16);
       aw.keys_out = (uint32_t*)cx.ensure(B_AFF_KEYS, az.rec * 4 + 16);
@@ -488,20 +534,32 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       // the LAST slice its bucket reduction and its share of the window combination follow on a high-priority stream
       // of their own, under the accumulation of the lower groups.
       CK(cudaEventRecord(cx.pl.ev_sorted, s));
-      for (int l = 0; l < nlanes; l++) CK(cudaStreamWaitEvent(cx.pl.big[l], cx.pl.ev_sorted, 0));
+      if (stagger) {
+        for (int j = 0; j < NG; j++) CK(cudaStreamWaitEvent(cx.pl.stag_big[j], cx.pl.ev_sorted, 0));
+      } else {
+        for (int l = 0; l < nlanes; l++) CK(cudaStreamWaitEvent(cx.pl.big[l], cx.pl.ev_sorted, 0));
+      }
       for (int g = NG - 1; g >= 0; g -= nlanes) {
         AffLanes ln{};
         ln.n = (g - 1 >= 0 && nlanes == 2) ? 2 : 1;
         ln.binv_stride = binv_stride;
         int gl[2] = {g, g - 1};
         for (int l = 0; l < ln.n; l++) {
-          int s1;
-          aff_group_range(nseg, NG, gl[l], ln.seg0[l], s1);
-          ln.segs[l] = s1 - ln.seg0[l];
-          ln.big[l] = cx.pl.big[l];
-          ln.chain[l] = cx.pl.chain[l];
-          ln.ev_a[l] = cx.pl.ev_a[l];
-          ln.ev_c[l] = cx.pl.ev_c[l];
+          ln.seg0[l] = grp0[gl[l]];
+          ln.segs[l] = grp0[gl[l] + 1] - grp0[gl[l]];
+          if (stagger) {
+            const int j = NG - 1 - g;   // lane 0 = top group = highest priority
+            ln.big[l] = cx.pl.stag_big[j];
+            ln.chain[l] = cx.pl.stag_chain[j];
+            ln.ev_a[l] = cx.pl.stag_a[j];
+            ln.ev_c[l] = cx.pl.stag_c[j];
+            ln.binv_base0 = (size_t)j * binv_stride;
+          } else {
+            ln.big[l] = cx.pl.big[l];
+            ln.chain[l] = cx.pl.chain[l];
+            ln.ev_a[l] = cx.pl.ev_a[l];
+            ln.ev_c[l] = cx.pl.ev_c[l];
+          }
         }
         if constexpr (HasAffineTree<C>::value) {
           if (R > 0)
@@ -563,10 +621,17 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         }
       }
       // the caller's stream resumes when the lanes are done (the next slice re-uses the pair arrays)
-      for (int l = 0; l < nlanes; l++) {
-        if (cx.pl.big[l] == s) continue;
-        CK(cudaEventRecord(cx.pl.ev_lane[l], cx.pl.big[l]));
-        CK(cudaStreamWaitEvent(s, cx.pl.ev_lane[l], 0));
+      if (stagger) {
+        for (int j = 0; j < NG; j++) {
+          CK(cudaEventRecord(cx.pl.stag_lane[j], cx.pl.stag_big[j]));
+          CK(cudaStreamWaitEvent(s, cx.pl.stag_lane[j], 0));
+        }
+      } else {
+        for (int l = 0; l < nlanes; l++) {
+          if (cx.pl.big[l] == s) continue;
+          CK(cudaEventRecord(cx.pl.ev_lane[l], cx.pl.big[l]));
+          CK(cudaStreamWaitEvent(s, cx.pl.ev_lane[l], 0));
+        }
       }
       CK(cudaEventRecord(ge[1], s));
       CK(cudaEventRecord(ge[2], s));
