@@ -42,8 +42,9 @@ EXECUTED_PER_AFFINE_ADD = {"bn128": 5 * 136 + 108, "bls12_381": 5 * 300 + 234}
 # dram__bytes_read.sum + dram__bytes_write.sum of the bucket-accumulation phase from an `ncu --set full` capture, keyed by
 # (curve, log2 n, affine levels); None where no capture exists.
 #   R = 0: ONE k_accumulate launch                      profiles/r1_e_ncu_k_accumulate_bls12381_2p20.txt
-#   R = 3: all kernels of the phase summed (tree + records)   profiles/r1_f_ncu_accumulate_phase_bls12381_2p20.txt
-NCU_TRAFFIC = {("bls12_381", 20, 0): 1.738798e9 + 0.172671e9}
+#   R = 3: all kernels of the phase summed (tree + records)   profiles/r1_g_ncu_accumulate_phase_bls12381_2p20.txt
+NCU_TRAFFIC = {("bls12_381", 20, 0): 1.738798e9 + 0.172671e9,
+               ("bls12_381", 20, 3): 7.393e9 + 2.057e9}
 METRIC = "G1 MSM throughput"
 UNIT = "points/s"
 

@@ -328,7 +328,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       // t = transfer time per point (measured: BN254 ~1.9/1.9 us per 1000 points, BLS12-381 5.4/2.6, G2 heavier)
       // Ordinary (pageable) memory goes through the staging ring at about half the PCIe rate, so t doubles.
       const bool pinned = host_is_pinned(points);
-      int pct = e ? atoi(e) : (pinned ? (L <= 8 ? 50 : (L <= 12 ? 33 : 25)) : (L <= 12 ? 50 : 35));   // measured (profiles/r1_notes.md)
+      int pct = e ? atoi(e) : (pinned ? (L <= 8 ? 50 : 25) : (L <= 12 ? 50 : 35));   // measured (profiles/r1_notes.md)
       if (pct < 5) pct = 5;
       if (pct > 95) pct = 95;
       lo[1] = (n * (size_t)pct / 100) & ~(size_t)3;
