@@ -365,9 +365,10 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       const char* e = getenv("ZKB200_AFFINE");
       if (e) {
         R = atoi(e);
-      } else if (L > 8 ? nmax >= ((size_t)1 << 19) : (nmax >= ((size_t)1 << 21) && nmax < ((size_t)1 << 23))) {
-        // 12 limbs: -12 % (2^20) .. -17 % (2^22, 2^24) of the whole MSM; 8 limbs: -3 % around 2^22, a loss at 2^24
-        // (the cheaper multiplication leaves the tree's extra memory traffic exposed)
+      } else if (L > 8 ? nmax >= ((size_t)1 << 19) : (nmax >= ((size_t)1 << 20) && nmax < ((size_t)1 << 22))) {
+        // 12 limbs: -7 % (2^19), -15 % (2^20), -22 % (2^21), -17 % (2^22, 2^24) of the whole MSM; 8 limbs: -7 % at 2^20,
+        // -2 % at 2^21, nothing at 2^22 and a loss at 2^24 (the cheaper multiplication leaves the tree's extra
+        // memory traffic exposed)
         R = ilog2_floor(nmax / NB + 1) - 2;
         if (pairs_max >= ((size_t)1 << 26)) R++;
         if (R > 5) R = 5;
