@@ -1,6 +1,6 @@
 """Build libzkmsm_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-Six translation units compiled in parallel (the fully unrolled 12-limb field code is slow to compile),
+Fourteen translation units compiled in parallel (the fully unrolled 12-limb field code is slow to compile),
 then linked into zikkurat_algebra_b200/lib/libzkmsm_b200.so with a static CUDA runtime.
 """
 from __future__ import annotations
