@@ -501,6 +501,18 @@ def test_g2_msm_next_row(zk, curve):
         want = refs.call_msm(lib, f"{curve}_G2_proj_MSM_std_coeff_affine_out", S, Pb.ravel(), W)
         got = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_std_coeff_affine_out", S, Pb)
         assert got.tobytes() == want.tobytes(), name
+        for R in (1, 2):   # the same shapes inside the batched-affine pre-reduction (Fp2 coordinates)
+            with _Env(ZKB200_AFFINE=R, ZKB200_WINDOW=3):
+                got = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_std_coeff_affine_out", S, Pb)
+            assert got.tobytes() == want.tobytes(), (name, R)
+    # the affine pre-reduction over Fp2, every lane mode
+    for n in (33, 257, 700):
+        pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=n + 5, reduce=True)
+        want = refs.call_msm(lib, f"{curve}_G2_proj_MSM_mont_coeff_affine_out", sc.ravel(), pts.ravel(), W, n=n)
+        for R, mode in ((1, {}), (3, {}), (5, dict(ZKB200_STAGGER=0)), (4, dict(ZKB200_STAGGER=4)), (2, dict(ZKB200_STAGGER=0, ZKB200_AFF_GROUPS=1))):
+            with _Env(ZKB200_AFFINE=R, **mode):
+                got = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_mont_coeff_affine_out", sc, pts, npoints=n)
+            assert got.tobytes() == want.tobytes(), (n, R, mode)
     # GPU chain generator for G2 == reference chain; larger size by the split property
     D = refs.call3(lib, f"{curve}_G2_affine_add", refs.call3(lib, f"{curve}_G2_affine_add", pts_all[0].copy(), pts_all[0].copy(), W), pts_all[0].copy(), W)
     assert zk.gen_chain(g2, 50, pts_all[0], D).tobytes() == pts_all[:50].tobytes()

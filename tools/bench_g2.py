@@ -24,8 +24,9 @@ for curve, logn in (("bn128", 16), ("bn128", 20), ("bls12_381", 16), ("bls12_381
         m = 1 << 12
         hp = pts[:m].cpu().numpy().view(np.uint64); hs = sc[:m].cpu().numpy().view(np.uint64)
         t0 = time.perf_counter(); refs.call_msm(lib, f"{curve}_G2_proj_MSM_mont_coeff_affine_out", hs.ravel(), hp.ravel(), W, n=m); cpu = (time.perf_counter() - t0)
-    row = dict(ms=best * 1e3, points_per_s=n / best, phase_ms=st["phase_ms"], window=st["window"], nwindows=st["nwindows"],
+    row = dict(affine_levels=st.get("affine_levels"), ms=best * 1e3, points_per_s=n / best, phase_ms=st["phase_ms"], window=st["window"], nwindows=st["nwindows"],
                reference_c_2p12_1core_ms=cpu * 1e3 if cpu else None)
     out[f"{g2}_2^{logn}"] = row
     print(g2, logn, json.dumps(row), flush=True)
-json.dump(out, open("gpurun_out/g2_bench.json", "w"), indent=1)
+import os
+json.dump(out, open("gpurun_out/g2_bench%s.json" % ("_R" + os.environ["ZKB200_AFFINE"] if "ZKB200_AFFINE" in os.environ else ""), "w"), indent=1)

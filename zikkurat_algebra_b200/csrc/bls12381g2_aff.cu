@@ -1,0 +1,5 @@
+// Bls12381G2: affine pre-reduction tree + record accumulation
+#include "kernels_aff.cuh"
+namespace zk {
+ZK_INSTANTIATE_AFF(Bls12381G2)
+}

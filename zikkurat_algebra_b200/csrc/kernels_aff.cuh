@@ -145,7 +145,9 @@ k_aff_prod(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
 // thread's shared-memory slot with cp.async while merge j is being computed, exactly like the point gather of
 // k_accumulate.  Slot layout [buffer][16-byte word][thread]: conflict-free.
 template <class P>
-constexpr int aff_stage_words() { return 2 * ((2 * P::L) / 4) + P::L / 4; }
+constexpr bool aff_stage_pre() { return P::L <= 16; }   // 24 limbs (BLS12-381 Fp2): the points alone fill the slot
+template <class P>
+constexpr int aff_stage_words() { return 2 * ((2 * P::L) / 4) + (aff_stage_pre<P>() ? P::L / 4 : 0); }
 template <class P>
 constexpr size_t aff_stage_bytes() { return (size_t)2 * aff_stage_words<P>() * AFF_THREADS * 16; }
 
@@ -156,7 +158,8 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
           const uint32_t* __restrict__ totinv, uint4* __restrict__ st_out, uint32_t* __restrict__ keys_out,
           uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets, int B) {
   using P = typename C::Fp;
-  constexpr int PW = (2 * P::L) / 4, FW = P::L / 4, NW = 2 * PW + FW;
+  constexpr bool SPRE = (P::L <= 16);
+  constexpr int PW = (2 * P::L) / 4, FW = SPRE ? P::L / 4 : 0, NW = 2 * PW + FW;
   extern __shared__ uint4 aff_stage[];   // [2][NW][AFF_THREADS]
   const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * B);
   Fe<P> r = ld_fe<P>(totinv + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L);
@@ -222,7 +225,8 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
         bool sinf = false;
         if (cls >= AFF_ADD) {
           Fe<P> pr;
-          staged(j & 1, 2 * PW, pr.l, FW);
+          if constexpr (SPRE) staged(j & 1, 2 * PW, pr.l, FW);
+          else pr = ld_fe<P>(pre + (size_t)m * P::L);
           Fe<P> dinv = aff_mul<P, CALLS>(r, pr);
           r = aff_mul<P, CALLS>(r, d);
           s = aff_finish<P, CALLS>(cls, p1, p2, dinv);

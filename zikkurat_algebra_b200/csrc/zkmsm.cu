@@ -238,6 +238,8 @@ struct DeviceGuard {  // run on our device, then give the caller its own current
 template <class C> struct HasAffineTree { static constexpr bool value = false; };
 template <> struct HasAffineTree<Bn254> { static constexpr bool value = true; };
 template <> struct HasAffineTree<Bls12381> { static constexpr bool value = true; };
+template <> struct HasAffineTree<Bn254G2> { static constexpr bool value = true; };
+template <> struct HasAffineTree<Bls12381G2> { static constexpr bool value = true; };
 
 int ilog2_floor(size_t x) { int r = 0; while (x > 1) { x >>= 1; r++; } return r; }
 
@@ -370,7 +372,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         // -2 % at 2^21, nothing at 2^22 and a loss at 2^24 (the cheaper multiplication leaves the tree's extra
         // memory traffic exposed)
         R = ilog2_floor(nmax / NB + 1) - 2;
-        if (pairs_max >= ((size_t)1 << 26)) R++;
+        if (pairs_max >= ((size_t)1 << 26) || L >= 16) R++;   // G2: heavier additions, one more level pays
         if (R > 5) R = 5;
       }
       if (R < 0) R = 0;
