@@ -150,10 +150,6 @@ struct AffLanes {
   size_t binv_base0;           // inversion workspace of lane 0 (elements from w.binv)
   size_t binv_stride;          // elements between the two lanes' inversion workspaces
 };
-inline void aff_group_range(int nseg, int groups, int g, int& s0, int& s1) {
-  s0 = (int)((long long)nseg * g / groups);
-  s1 = (int)((long long)nseg * (g + 1) / groups);
-}
 // R levels of pairwise affine sums over the sorted pairs of the lanes' segments, then the XYZZ accumulation of the
 // surviving records (chunk_rec record slots per thread, cps threads per segment; heads / head_keys indexed by segment
 // as for launch_accumulate).  keys / vals / buckets / heads are the arrays of ALL segments.
