@@ -481,7 +481,8 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     int log_m1 = 0;
     if (c - 1 > 0) {
       const char* e = getenv("ZKB200_LOGM1");
-      log_m1 = e ? atoi(e) : ilog2_floor(((size_t)nseg << (c - 1)) / 32768 + 1);   // about one wave of threads (measured)
+      // about one wave of threads per launch (measured); with window groups the biggest launch has half the segments
+      log_m1 = e ? atoi(e) : ilog2_floor(((size_t)(split_tail ? (nseg + 1) / 2 : nseg) << (c - 1)) / 32768 + 1);
       if (log_m1 < 1) log_m1 = 1;
       if (log_m1 > 5) log_m1 = 5;
       if (log_m1 > c - 1) log_m1 = c - 1;
