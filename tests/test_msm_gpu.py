@@ -768,3 +768,31 @@ def test_affine_pre_reduction_mid_size_vs_threaded_reference(zk):
         with _Env(ZKB200_AFFINE=R):
             got = zk.msm(curve, sc, pts, mont=True, out="affine")
         assert got.tobytes() == want, R
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_repeated_large_calls_are_stable(zk, curve):
+    """The default large-n path runs several streams at once (lanes of the affine pre-reduction, per-group reduction
+    and window combination).  A missing dependency between them would show up as an occasional wrong answer:
+    repeat the same 2^19-point MSM, resident and from host buffers, and compare with the single-stream XYZZ path."""
+    import torch
+    n = 1 << 19
+    cv = pyec.CURVES[curve]
+    p0 = np.frombuffer(cv.affine_to_bytes(cv.mul(0x1234567, cv.gen)), dtype=np.uint64).copy()
+    d = np.frombuffer(cv.affine_to_bytes(cv.mul(0x7654321, cv.gen)), dtype=np.uint64).copy()
+    pts = torch.empty((n, 2 * cv.nlimbs_p), dtype=torch.int64, device="cuda")
+    zk.gen_chain(curve, n, p0, d, device_ptr=pts.data_ptr())
+    sc = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda")
+    sc[:, 3] &= (1 << 61) - 1
+    torch.cuda.synchronize()
+    with _Env(ZKB200_AFFINE=0, ZKB200_WGROUPS=1, ZKB200_AFF_GROUPS=1):
+        want = zk.msm_device(curve, sc.data_ptr(), pts.data_ptr(), n, mont=True, out="affine")[0].tobytes()
+    h_pts, h_sc = pts.cpu().numpy().view(np.uint64), sc.cpu().numpy().view(np.uint64)
+    for mode in (dict(ZKB200_AFFINE=3), dict(ZKB200_AFFINE=3, ZKB200_STAGGER=4), dict(ZKB200_AFFINE=4, ZKB200_STAGGER=0),
+                 dict(ZKB200_AFFINE=0)):
+        with _Env(**mode):
+            for rep in range(8):
+                got = zk.msm_device(curve, sc.data_ptr(), pts.data_ptr(), n, mont=True, out="affine")[0].tobytes()
+                assert got == want, (mode, rep)
+            for rep in range(3):
+                assert zk.msm(curve, h_sc, h_pts, mont=True, out="affine").tobytes() == want, (mode, "host", rep)
