@@ -173,6 +173,10 @@ void zkb200_set_devices(const int *devices, int count);
 /* Phase timings (CUDA events, ms) of the most recent zkb200_msm on this thread's device:
  *  [0] h2d scalars  [1] recode  [2] sort  [3] wait for points h2d  [4] accumulate  [5] fixup
  *  [6] reduce  [7] tail + d2h   [8] total on the compute stream.
+ * The accumulation runs on several streams (lanes); the phases are what the caller's stream sees:
+ *  [4] = until every lane has finished (affine pre-reduction, XYZZ accumulation AND the fix-up tree, so [5] ~ 0),
+ *  [6] = what is left of the per-group bucket reduction / window combination after that point (the rest ran under
+ *  the accumulation), [7] = sum of the groups' shares, output conversion, D2H.
  * Also: window width c, number of windows W, insertions n*W, of the same call. */
 void zkb200_last_stats(float phase_ms[9], int *window_c, int *nwindows, long long *insertions);
 /* levels of the batched-affine pre-reduction the last MSM on the current device used (0 = plain XYZZ accumulation) */
