@@ -52,6 +52,13 @@ def test_fp_ops(he, curve):
         assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv", A, L).tobytes()) == pow(a, -1, cv.p)
         assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv_fermat", A, L).tobytes()) == pow(a, -1, cv.p)
         assert cv.fp_from_bytes(refs.call2(he, f"he_{curve}_fp_inv_euclid", A, L).tobytes()) == pow(a, -1, cv.p)
+    # raw residues whose low limbs are zero: the multi-bit halving must cope with 32 and more trailing zero bits
+    for x in [1 << 32, 1 << 64, 3 << 96, (1 << 160) + (1 << 128), 5 << 224, (cv.p - 1) & ~((1 << 70) - 1)]:
+        x %= cv.p
+        A = _arr(x.to_bytes(8 * L, "little"))
+        want = pow(x, -1, cv.p) * cv.R * cv.R % cv.p
+        for f in ("fp_inv", "fp_inv_euclid"):
+            assert int.from_bytes(refs.call2(he, f"he_{curve}_{f}", A, L).tobytes(), "little") == want, (f, hex(x))
     # the same inversion over Fr (NTT scaling, batch inversion users): raw residues, R = 2^256
     Rr = 1 << 256
     for a in [1, 2, 3, cv.r - 1, cv.r - 2, (cv.r + 1) // 2, 1 << 200] + [rng.randrange(1, cv.r) for _ in range(300)]:

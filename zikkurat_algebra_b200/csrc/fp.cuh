@@ -497,6 +497,36 @@ ZK_HD Fe<P> fe_pow2(int e) {  // 2^e as a plain integer, e < 32L
   for (int i = 0; i < P::L; i++) r.l[i] = (i == (e >> 5)) ? (1u << (e & 31)) : 0u;
   return r;
 }
+// multi-bit shifts, 1 <= t <= 31
+ZK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int t) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, t);
+#else
+  return (lo >> t) | (hi << (32 - t));
+#endif
+}
+ZK_HD int ctz32(uint32_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+template <int L>
+ZK_HD void big_shr(uint32_t* a, int t) {
+#pragma unroll
+  for (int i = 0; i < L - 1; i++) a[i] = funnel_r(a[i], a[i + 1], t);
+  a[L - 1] >>= t;
+}
+template <int L>
+ZK_HD void big_shl(uint32_t* a, int t) {
+#pragma unroll
+  for (int i = L - 1; i > 0; i--) a[i] = funnel_r(a[i - 1], a[i], 32 - t);
+  a[0] <<= t;
+}
+// trailing zero bits of a non-zero multi-limb value, capped at 31 (the caller loops)
+ZK_HD int low_zeros(uint32_t limb0) { return limb0 ? ctz32(limb0) : 31; }
+
 template <class P>
 ZK_HD Fe<P> fe_inv(const Fe<P>& a) {  // a != 0, canonical; returns the Montgomery form of 1/a
   constexpr int L = P::L;
@@ -505,39 +535,43 @@ ZK_HD Fe<P> fe_inv(const Fe<P>& a) {  // a != 0, canonical; returns the Montgome
   for (int i = 0; i < L; i++) { u[i] = P::mod(i); v[i] = a.l[i]; r[i] = 0; s[i] = 0; }
   s[0] = 1;
   int k = 0;
-  for (; k < 2 * P::BITS + 2; k++) {
+  // Every trip ends with u and v odd again: all the halvings that follow a subtraction are done at once
+  // (count trailing zeros), so a trip is one subtraction, one addition and two multi-bit shifts.
+  for (int guard = 0; guard < 2 * P::BITS + 2; guard++) {
     if (big_is_zero<L>(v)) break;
     if ((u[0] & 1u) == 0) {
-      big_shr1<L>(u, 0u);
-      big_shl1<L>(s);
-    } else if ((v[0] & 1u) == 0) {
-      big_shr1<L>(v, 0u);
-      big_shl1<L>(r);
-    } else {
-      uint32_t d1[L], d2[L], rs[L];   // u - v, v - u, r + s: three independent carry chains
-      d1[0] = sub_cc(u[0], v[0]);
+      const int t = low_zeros(u[0]);
+      big_shr<L>(u, t); big_shl<L>(s, t); k += t;
+      continue;
+    }
+    if ((v[0] & 1u) == 0) {
+      const int t = low_zeros(v[0]);
+      big_shr<L>(v, t); big_shl<L>(r, t); k += t;
+      continue;
+    }
+    uint32_t d[L], rs[L];   // u - v and r + s: independent carry chains
+    d[0] = sub_cc(u[0], v[0]);
 #pragma unroll
-      for (int i = 1; i < L; i++) d1[i] = subc_cc(u[i], v[i]);
-      const bool v_ge_u_strict_or_eq = subc(0u, 0u) != 0u;   // borrow: u < v
-      d2[0] = sub_cc(v[0], u[0]);
+    for (int i = 1; i < L; i++) d[i] = subc_cc(u[i], v[i]);
+    const bool u_lt_v = subc(0u, 0u) != 0u;
+    rs[0] = add_cc(r[0], s[0]);
 #pragma unroll
-      for (int i = 1; i < L; i++) d2[i] = subc_cc(v[i], u[i]);
-      rs[0] = add_cc(r[0], s[0]);
+    for (int i = 1; i < L - 1; i++) rs[i] = addc_cc(r[i], s[i]);
+    rs[L - 1] = addc(r[L - 1], s[L - 1]);
+    if (!u_lt_v && !big_is_zero<L>(d)) {   // u > v:  u = (u - v) / 2^t,  r = r + s,  s = s * 2^t
+      const int t = low_zeros(d[0]);
 #pragma unroll
-      for (int i = 1; i < L - 1; i++) rs[i] = addc_cc(r[i], s[i]);
-      rs[L - 1] = addc(r[L - 1], s[L - 1]);
-      const bool u_gt_v = !v_ge_u_strict_or_eq && !big_is_zero<L>(d1);
-      if (u_gt_v) {
+      for (int i = 0; i < L; i++) { u[i] = d[i]; r[i] = rs[i]; }
+      big_shr<L>(u, t); big_shl<L>(s, t); k += t;
+    } else {                               // v >= u: v = (v - u) / 2^t,  s = s + r,  r = r * 2^t
+      v[0] = sub_cc(v[0], u[0]);
 #pragma unroll
-        for (int i = 0; i < L; i++) { u[i] = d1[i]; r[i] = rs[i]; }
-        big_shr1<L>(u, 0u);
-        big_shl1<L>(s);
-      } else {
+      for (int i = 1; i < L; i++) v[i] = subc_cc(v[i], u[i]);
 #pragma unroll
-        for (int i = 0; i < L; i++) { v[i] = d2[i]; s[i] = rs[i]; }
-        big_shr1<L>(v, 0u);
-        big_shl1<L>(r);
-      }
+      for (int i = 0; i < L; i++) s[i] = rs[i];
+      if (big_is_zero<L>(v)) { big_shl1<L>(r); k += 1; break; }   // u == v == 1: the last step halves a zero
+      const int t = low_zeros(v[0]);
+      big_shr<L>(v, t); big_shl<L>(r, t); k += t;
     }
   }
   // r < 2p:  x = p - (r mod p)

@@ -305,12 +305,30 @@ template <class P, int G = BINV_G>
 ZK_D Fe<P> binv_thread_up(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE, uint32_t t) {
   constexpr bool CALLS = (P::L > 8);
   Fe<P> run = fe_one<P>();
+  if constexpr (G <= 4) {
+    // latency-bound levels: all loads first, then the dependent products
+    Fe<P> e[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      const size_t idx = (size_t)t * G + k;
+      e[k] = idx < T ? ld_fe<P>(E + idx * P::L) : fe_one<P>();
+    }
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      const size_t idx = (size_t)t * G + k;
+      if (idx < T) {
+        st_fe<P>(PRE + idx * P::L, run);
+        run = aff_mul<P, CALLS>(run, e[k]);
+      }
+    }
+  } else {
 #pragma unroll 1
-  for (int k = 0; k < G; k++) {
-    const size_t idx = (size_t)t * G + k;
-    if (idx < T) {
-      st_fe<P>(PRE + idx * P::L, run);
-      run = aff_mul<P, CALLS>(run, ld_fe<P>(E + idx * P::L));
+    for (int k = 0; k < G; k++) {
+      const size_t idx = (size_t)t * G + k;
+      if (idx < T) {
+        st_fe<P>(PRE + idx * P::L, run);
+        run = aff_mul<P, CALLS>(run, ld_fe<P>(E + idx * P::L));
+      }
     }
   }
   return run;
@@ -318,13 +336,30 @@ ZK_D Fe<P> binv_thread_up(const uint32_t* __restrict__ E, uint32_t T, uint32_t* 
 template <class P, int G = BINV_G>
 ZK_D void binv_thread_down(const uint32_t* __restrict__ E, uint32_t T, uint32_t* __restrict__ PRE, uint32_t t, Fe<P> r) {
   constexpr bool CALLS = (P::L > 8);
+  if constexpr (G <= 4) {
+    Fe<P> e[G], p[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      const size_t idx = (size_t)t * G + k;
+      if (idx < T) { p[k] = ld_fe<P>(PRE + idx * P::L); e[k] = ld_fe<P>(E + idx * P::L); }
+    }
+#pragma unroll
+    for (int k = G - 1; k >= 0; k--) {
+      const size_t idx = (size_t)t * G + k;
+      if (idx < T) {
+        st_fe<P>(PRE + idx * P::L, aff_mul<P, CALLS>(r, p[k]));
+        if (k > 0) r = aff_mul<P, CALLS>(r, e[k]);
+      }
+    }
+  } else {
 #pragma unroll 1
-  for (int k = G - 1; k >= 0; k--) {
-    const size_t idx = (size_t)t * G + k;
-    if (idx < T) {
-      Fe<P> p = ld_fe<P>(PRE + idx * P::L), e = ld_fe<P>(E + idx * P::L);
-      st_fe<P>(PRE + idx * P::L, aff_mul<P, CALLS>(r, p));
-      r = aff_mul<P, CALLS>(r, e);
+    for (int k = G - 1; k >= 0; k--) {
+      const size_t idx = (size_t)t * G + k;
+      if (idx < T) {
+        Fe<P> p = ld_fe<P>(PRE + idx * P::L), e = ld_fe<P>(E + idx * P::L);
+        st_fe<P>(PRE + idx * P::L, aff_mul<P, CALLS>(r, p));
+        r = aff_mul<P, CALLS>(r, e);
+      }
     }
   }
 }
