@@ -400,7 +400,8 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // Staggered mode (needs the tree's short-lived blocks): every group gets its own lane, upper windows at higher
     // stream priority, so the upper groups finish first -- their reduction and their long doubling chains then run
     // under the lower groups' work -- while each lane's inversion chains hide behind the lower-priority lanes.
-    // Groups from the bottom: [0, W/4), [W/4, W/2), [W/2, W)  ($ZKB200_STAGGER = number of groups 2..4, 0 = off).
+    // Groups from the bottom: [0, 3W/16), [3W/16, 9W/16), [9W/16, W)  ($ZKB200_STAGGER = number of groups 2..4,
+    // 0 = off; $ZKB200_STAGGER_SPLIT = the inner boundaries in windows).
     int stagger = 0;
     if (nmsm == 1 && W >= 8 && R > 0) {
       const char* e = getenv("ZKB200_STAGGER");
@@ -431,8 +432,22 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     if (!split_tail) NG = nlanes;   // without the split the lanes simply halve the segments
     int grp0[9];                    // group g covers segments [grp0[g], grp0[g+1]), bottom windows first
     for (int g = 0; g <= NG; g++) {
-      if (stagger) grp0[g] = g == 0 ? 0 : (g == NG ? W : (W >> (NG - g)));
+      if (stagger == 3) grp0[g] = g == 0 ? 0 : (g == 3 ? W : ((g == 1 ? 3 : 9) * W + 8) / 16);   // measured best: 3/16, 9/16
+      else if (stagger) grp0[g] = g == 0 ? 0 : (g == NG ? W : (W >> (NG - g)));
       else grp0[g] = (int)((long long)nseg * g / NG);
+    }
+    if (stagger) {   // $ZKB200_STAGGER_SPLIT = "a,b,..": inner group boundaries in windows, bottom first (NG - 1 values)
+      const char* e = getenv("ZKB200_STAGGER_SPLIT");
+      if (e) {
+        int g = 1;
+        for (const char* q = e; *q && g < NG; g++) {
+          int v = atoi(q);
+          if (v > grp0[g - 1] && v < W) grp0[g] = v;
+          while (*q && *q != ',') q++;
+          if (*q == ',') q++;
+        }
+        for (g = 1; g < NG; g++) if (grp0[g] <= grp0[g - 1]) grp0[g] = grp0[g - 1] + 1;
+      }
     }
     const int conc_segs = stagger ? nseg : (nseg + NG - 1) / NG * nlanes;   // segments in flight at a time
     auto pick_chunk = [&](size_t per_seg) -> int {
