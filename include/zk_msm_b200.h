@@ -141,6 +141,17 @@ void zkb200_msm(int curve, int nmsm, long npoints, const uint64_t *scalars, int 
  * (in_mode: PROJ, JAC or XYZZ records in host memory). */
 void zkb200_sum_points(int curve, int k, const uint64_t *in, int in_mode, int out_mode, uint64_t *out);
 
+/* The same two calls with the result / the operands in DEVICE memory of the current device, so that a multi-GPU
+ * run keeps its partial points on the GPUs: zkb200_msm_ex writes the nmsm result records to `out` (out_loc =
+ * ZKB200_DEVICE: device-to-device, nothing but the completion wait touches the host), a collective (NCCL all-gather over
+ * NVLink, see zikkurat_algebra_b200/distributed.py) moves them, zkb200_sum_points_ex reads the k records from device
+ * memory (in_loc = ZKB200_DEVICE) and returns the sum in host memory.  With *_loc = ZKB200_HOST they are zkb200_msm /
+ * zkb200_sum_points. */
+void zkb200_msm_ex(int curve, int nmsm, long npoints, const uint64_t *scalars, int scalars_loc,
+                   const uint64_t *points, int points_loc, int expo_nlimbs, int mont_coeff, int out_mode,
+                   int window, uint64_t *out, int out_loc);
+void zkb200_sum_points_ex(int curve, int k, const uint64_t *in, int in_loc, int in_mode, int out_mode, uint64_t *out);
+
 /* Workload synthesis on the GPU (not part of the MSM path): out[i] = P0 + (start + i) * D for
  * i < n as canonical affine Montgomery points, written to host (out_loc = ZKB200_HOST) or device memory.
  * Used by bench.py and the tests to build large synthetic point arrays. */
@@ -158,6 +169,37 @@ void zkb200_ntt(int curve, int m, const uint64_t *gen, const uint64_t *src, int 
  * zkb200_msm / zkb200_ntt with location ZKB200_DEVICE.  Free it with zkb200_device_free. */
 void *zkb200_device_upload(const void *host, size_t bytes);
 void zkb200_device_free(void *device_ptr);
+
+/* Resident point arrays ("SRS cache").  Every entry point that takes a HOST point array keeps a copy of it on the
+ * device after the first call, keyed by (host pointer, byte count, curve) and guarded by a 64-bit fingerprint of a strided
+ * sample of its words; later calls over the same array (the SRS of a KZG prover: examples/KZG.hs:77-88,110-116) move only
+ * the scalars.  Budget per device: $ZKB200_SRS_CACHE_MB (default 16384, 0 = off), least recently used arrays go first.
+ * The reference's point arrays are immutable (lib/src/ZK/Algebra/Class/Flat.hs:81-90); a C caller that rewrites a few
+ * points of an array IN PLACE between calls must disable the cache (or pass a fresh buffer), because the fingerprint
+ * samples about 1500 words, not all of them.  zkb200_last_srs_hit: 1 when the last MSM on the current device used a
+ * resident copy. */
+int zkb200_last_srs_hit(void);
+/* forget every resident point array on every device (the next call over an array uploads it again) */
+void zkb200_srs_cache_drop(void);
+
+/* Give back all device memory this library holds on every device it has used (work arrays that only grow otherwise,
+ * the pinned result buffer, the resident point arrays).  The next call allocates again.  A work-array allocation
+ * that fails first drops the resident point arrays and retries; batches that would not fit are processed in halves;
+ * only then does the library give up (message + abort(), the reference's convention for malloc failure). */
+void zkb200_release_workspaces(void);
+
+/* Element-wise self-tests of the device primitives, used by tests/test_device_primitives.py to compare the compiled
+ * PTX carry chains with the reference's field and group functions operand by operand (not part of the MSM path).
+ * field: 0 = bn128 Fp, 1 = bls12_381 Fp, 2 = bn128 Fr, 3 = bls12_381 Fr;  op: 0 mul, 1 sqr, 2 a*b+c*d, 3 add, 4 sub, 5 neg,
+ * 6 inv (0 -> 0), 7..9 = 0..2 through the out-of-line multiplication, 10 double, 11 Montgomery -> standard form.
+ * n elements of 4/6 uint64 limbs per operand (b, c, d may be NULL where unused).
+ * group op: 0 XYZZ += affine, 1 the same with out-of-line multiplications, 2 XYZZ + XYZZ, 3 the same out of line,
+ * 4 double, 5 double of an affine point.  Operand k is the affine point p_k (all 0xFF = infinity) lifted with the
+ * scale z_k to (x z^2, y z^3, z^2, z^3); results are canonical affine records. */
+void zkb200_selftest_field(int field, int op, long n, const uint64_t *a, const uint64_t *b, const uint64_t *c,
+                           const uint64_t *d, uint64_t *out);
+void zkb200_selftest_group(int curve, int op, long n, const uint64_t *p1, const uint64_t *z1, const uint64_t *p2,
+                           const uint64_t *z2, uint64_t *out_affine);
 
 /* Number of kernels this library has launched since it was loaded (bench.py's "gpu_launches"). */
 long long zkb200_launch_count(void);
@@ -183,8 +225,9 @@ void zkb200_last_stats(float phase_ms[9], int *window_c, int *nwindows, long lon
 int zkb200_last_affine_levels(void);
 
 /* Register-resident integer-multiply throughput probe: returns 32x32-bit products per second of the
- * whole GPU for kind 0 = mad.lo/madc.hi carry chains (as used by the field code), 1 = mad.wide.u32,
- * 2 = mad.lo.u32 only.  Used for the IMAD roofline denominator. */
+ * whole GPU for kind 0 = mad.lo/madc.hi carry chains (as used by the field code), 1 = mad.wide.u32 with a 64-bit
+ * accumulator and no carry, 2 = 32-bit mad.lo.u32 only, 3 = mul.wide.u32 (product only).  Every repetition uses its own
+ * multiplier so that ptxas cannot reuse a product.  Used for the IMAD roofline denominator. */
 double zkb200_imad_peak(int kind, int iters);
 
 const char *zkb200_version(void);

@@ -117,19 +117,58 @@ def random_scalars(curve: str, n: int, seed: int, mont: bool = False, reduce: bo
     return np.ascontiguousarray(a)
 
 
-def chain_points(curve: str, n: int, s0: int = 0x1234567, s1: int = 0x7654321) -> np.ndarray:
-    """(n, 2L) uint64 affine Montgomery points P_i = (s0 + i*s1)*G via the oracle's chain generator."""
+def counter_scalars(seed: int, start: int, n: int, bits: int = 253) -> np.ndarray:
+    """Scalars of a GLOBAL workload as a pure function of (seed, global index): limb j of scalar i is
+    splitmix64(seed * 2^32 + 4*i + j), the top limb cut so that the value is < 2^bits (253: < r for both
+    curves, so the same words serve as a standard integer or as a Montgomery representative).  Any rank
+    regenerates exactly its slice [start, start + n); tests/golden/make_big_golden.py generates the whole
+    vector with the same function.  Returns (n, 4) uint64."""
+    with np.errstate(over="ignore"):
+        idx = (np.arange(start * 4, (start + n) * 4, dtype=np.uint64) + np.uint64((seed << 32) & 0xFFFFFFFFFFFFFFFF))
+        z = idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    a = z.reshape(n, 4)
+    if bits < 256:
+        a[:, 3] &= np.uint64((1 << (bits - 192)) - 1)
+    return np.ascontiguousarray(a)
+
+
+def chain_base(curve: str, s0: int = 0x1234567, s1: int = 0x7654321, start: int = 0):
+    """(P_start, D) of the global point chain P_i = (s0 + i*s1)*G as affine Montgomery limbs (Python big ints only)."""
     from . import pyec  # local import: tests package
     cv = pyec.CURVES[curve]
-    L = cv.nlimbs_p
-    p0 = np.frombuffer(cv.affine_to_bytes(cv.mul(s0, cv.gen)), dtype=np.uint64).copy()
+    p0 = np.frombuffer(cv.affine_to_bytes(cv.mul(s0 + start * s1, cv.gen)), dtype=np.uint64).copy()
     d = np.frombuffer(cv.affine_to_bytes(cv.mul(s1, cv.gen)), dtype=np.uint64).copy()
+    return p0, d
+
+
+def chain_points(curve: str, n: int, s0: int = 0x1234567, s1: int = 0x7654321, start: int = 0, nthreads: int = 1) -> np.ndarray:
+    """(n, 2L) uint64 affine Montgomery points P_i = (s0 + (start + i)*s1)*G via the oracle's chain generator
+    (`nthreads` > 1: contiguous blocks, each started from its own multiple of G)."""
+    import threading
+    L = CURVE_LIMBS[curve]
     out = np.zeros((n, 2 * L), dtype=np.uint64)
     f = getattr(oracle(), f"zko_{curve}_gen_chain")
     f.argtypes = [ctypes.c_long, U64P, U64P, U64P]
     f.restype = None
-    if n:
-        f(n, ptr(p0), ptr(d), ptr(out))
+    if n == 0:
+        return out
+    nthreads = max(1, min(nthreads, n // 4096 or 1))
+    bounds = [n * k // nthreads for k in range(nthreads + 1)]
+    bases = [chain_base(curve, s0, s1, start + bounds[k]) for k in range(nthreads)]
+
+    def work(k):
+        lo, hi = bounds[k], bounds[k + 1]
+        if hi > lo:
+            f(hi - lo, ptr(bases[k][0]), ptr(bases[k][1]), out[lo:hi].ctypes.data_as(U64P))
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
     return out
 
 

@@ -21,6 +21,7 @@ import numpy as np
 __all__ = [
     "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "G2_SYMBOLS", "GFFT_SYMBOLS", "EXTRA_SYMBOLS", "group_fft", "call_reference_symbol",
     "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "ResidentPoints", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
+    "msm_to_device", "sum_points_device", "last_srs_hit", "release_workspaces", "srs_cache_drop", "selftest_field", "selftest_group", "FIELD_OPS", "GROUP_OPS",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -49,7 +50,13 @@ EXTRA_SYMBOLS = ([f"{c}_G2_proj_batch_{d}_affine" for c in ("bn128", "bls12_381"
                  [f"{c}_{g}_out_slow_reference" for c in ("bn128", "bls12_381")
                   for g in ("G1_proj_MSM_std_coeff_proj", "G1_jac_MSM_std_coeff_jac", "G2_proj_MSM_std_coeff_proj")])
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
-                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt", "zkb200_device_upload", "zkb200_device_free", "zkb200_last_affine_levels"]
+                     "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt", "zkb200_device_upload", "zkb200_device_free", "zkb200_last_affine_levels",
+                     "zkb200_msm_ex", "zkb200_sum_points_ex", "zkb200_last_srs_hit", "zkb200_srs_cache_drop", "zkb200_release_workspaces",
+                     "zkb200_selftest_field", "zkb200_selftest_group"]
+FIELD_IDS = {("bn128", "Fp"): 0, ("bls12_381", "Fp"): 1, ("bn128", "Fr"): 2, ("bls12_381", "Fr"): 3}
+FIELD_OPS = {"mul": 0, "sqr": 1, "mul2": 2, "add": 3, "sub": 4, "neg": 5, "inv": 6, "mul_call": 7, "sqr_call": 8, "mul2_call": 9,
+             "dbl": 10, "from_mont": 11}
+GROUP_OPS = {"madd": 0, "madd_calls": 1, "add": 2, "add_calls": 3, "dbl": 4, "dbl_affine": 5}
 
 _U64P = ctypes.POINTER(ctypes.c_uint64)
 _lib: Optional[ctypes.CDLL] = None
@@ -73,6 +80,16 @@ def lib() -> ctypes.CDLL:
         L.zkb200_msm.restype = None
         L.zkb200_sum_points.argtypes = [ctypes.c_int, ctypes.c_int, _U64P, ctypes.c_int, ctypes.c_int, _U64P]
         L.zkb200_sum_points.restype = None
+        L.zkb200_msm_ex.argtypes = L.zkb200_msm.argtypes[:-1] + [ctypes.c_void_p, ctypes.c_int]
+        L.zkb200_msm_ex.restype = None
+        L.zkb200_sum_points_ex.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _U64P]
+        L.zkb200_sum_points_ex.restype = None
+        L.zkb200_last_srs_hit.restype = ctypes.c_int
+        L.zkb200_release_workspaces.restype = None
+        L.zkb200_selftest_field.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long] + [ctypes.c_void_p] * 4 + [_U64P]
+        L.zkb200_selftest_field.restype = None
+        L.zkb200_selftest_group.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_long] + [ctypes.c_void_p] * 4 + [_U64P]
+        L.zkb200_selftest_group.restype = None
         L.zkb200_set_device.argtypes = [ctypes.c_int]
         L.zkb200_set_device.restype = None
         L.zkb200_last_stats.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int),
@@ -122,8 +139,21 @@ def set_device(device: int) -> None:
     lib().zkb200_set_device(int(device))
 
 
+def _device_count() -> int:
+    try:
+        import torch
+        return int(torch.cuda.device_count())
+    except Exception:          # torch is optional plumbing: without it the library itself rejects bad indices
+        return 1 << 30
+
+
 def set_devices(devices) -> None:
     """Shard every subsequent host-buffer call over these GPUs from inside the library ([] = single device)."""
+    devices = [int(d) for d in devices]
+    cnt = _device_count()
+    for d in devices:
+        if d < 0 or d >= cnt:
+            raise ValueError(f"device index {d} out of range (visible devices: {cnt})")
     arr = (ctypes.c_int * max(1, len(devices)))(*devices)
     lib().zkb200_set_devices(arr, len(devices))
 
@@ -156,7 +186,11 @@ def msm_batch(curve: str, scalars: np.ndarray, points: np.ndarray, mont: bool = 
     cv = CURVES[curve]
     s = _as_u64(scalars)
     p = _as_u64(points)
+    if s.ndim != 3 or s.shape[2] != expo_nlimbs:
+        raise ValueError(f"scalars must have shape (nmsm, n, {expo_nlimbs}), got {s.shape}")
     nmsm, n = s.shape[0], s.shape[1]
+    if p.size != n * 2 * cv["nlimbs_p"]:
+        raise ValueError(f"points must hold n = {n} records of {2 * cv['nlimbs_p']} uint64 words, got {p.size} words")
     mode = _OUT[out]
     res = np.zeros((nmsm, _OUT_COORDS[mode] * cv["nlimbs_p"]), dtype=np.uint64)
     lib().zkb200_msm(cv["id"], nmsm, n, s.ctypes.data if s.size else None, HOST, p.ctypes.data if p.size else None, HOST,
@@ -185,6 +219,70 @@ def msm_device(curve: str, scalars_ptr: int, points_ptr: int, npoints: int, nmsm
     lib().zkb200_msm(cv["id"], nmsm, npoints, scalars_ptr, DEVICE, points_ptr, DEVICE, expo_nlimbs, int(mont), mode,
                      window, _ptr(res))
     return res
+
+
+def msm_to_device(curve: str, scalars, points, npoints: int, out_ptr: int, nmsm: int = 1, mont: bool = True, out: str = "xyzz",
+                  window: int = 0, resident: bool = True, expo_nlimbs: int = 4) -> None:
+    """MSM whose result record(s) stay in DEVICE memory at `out_ptr` (multi-GPU combine without a host bounce).
+    `resident`: scalars / points are raw device pointers; else host arrays."""
+    cv = CURVES[curve]
+    if resident:
+        sp, pp, loc = scalars, points, DEVICE
+    else:
+        s, p = _as_u64(scalars), _as_u64(points)
+        if s.size != nmsm * npoints * expo_nlimbs or p.size != npoints * 2 * cv["nlimbs_p"]:
+            raise ValueError("scalars / points do not match npoints")
+        sp, pp, loc = s.ctypes.data, p.ctypes.data, HOST
+    lib().zkb200_msm_ex(cv["id"], nmsm, npoints, sp, loc, pp, loc, expo_nlimbs, int(mont), _OUT[out], window, out_ptr, DEVICE)
+
+
+def sum_points_device(curve: str, in_ptr: int, k: int, in_repr: str = "xyzz", out: str = "affine") -> np.ndarray:
+    """Sum of k group elements that already sit in the current device's memory (e.g. an NCCL all-gather output)."""
+    cv = CURVES[curve]
+    mode = _OUT[out]
+    res = np.zeros(_OUT_COORDS[mode] * cv["nlimbs_p"], dtype=np.uint64)
+    lib().zkb200_sum_points_ex(cv["id"], k, in_ptr, DEVICE, _OUT[in_repr], mode, _ptr(res))
+    return res
+
+
+def last_srs_hit() -> bool:
+    """True when the most recent MSM on the current device took its points from the resident-copy cache."""
+    return bool(lib().zkb200_last_srs_hit())
+
+
+def release_workspaces() -> None:
+    lib().zkb200_release_workspaces()
+
+
+def srs_cache_drop() -> None:
+    """Forget every resident point array (the next call over an array uploads it again)."""
+    lib().zkb200_srs_cache_drop()
+
+
+def selftest_field(curve: str, field: str, op: str, a: np.ndarray, b=None, c=None, d=None) -> np.ndarray:
+    """Element-wise device field operation on (n, limbs) uint64 arrays (tests only; see zkb200_selftest_field)."""
+    a = _as_u64(a)
+    arrs = [a] + [None if x is None else _as_u64(x) for x in (b, c, d)]
+    for x in arrs[1:]:
+        if x is not None and x.shape != a.shape:
+            raise ValueError("operand shapes differ")
+    out = np.zeros_like(a)
+    lib().zkb200_selftest_field(FIELD_IDS[(curve, field)], FIELD_OPS[op], a.shape[0],
+                                *[None if x is None else x.ctypes.data for x in arrs], _ptr(out.ravel()))
+    return out
+
+
+def selftest_group(curve: str, op: str, p1: np.ndarray, z1: np.ndarray, p2: np.ndarray, z2: np.ndarray) -> np.ndarray:
+    """Element-wise device group operation (tests only; see zkb200_selftest_group) -> (n, 2L) canonical affine."""
+    p1, z1, p2, z2 = (_as_u64(x) for x in (p1, z1, p2, z2))
+    n = p1.shape[0]
+    L = CURVES[curve]["nlimbs_p"]
+    if p1.shape != (n, 2 * L) or p2.shape != (n, 2 * L) or z1.shape != (n, L) or z2.shape != (n, L):
+        raise ValueError("selftest_group: operand shapes")
+    out = np.zeros((n, 2 * L), dtype=np.uint64)
+    lib().zkb200_selftest_group(CURVES[curve]["id"], GROUP_OPS[op], n, p1.ctypes.data, z1.ctypes.data, p2.ctypes.data, z2.ctypes.data,
+                                _ptr(out.ravel()))
+    return out
 
 
 def ntt(curve: str, m: int, gen: np.ndarray, src: np.ndarray, inverse: bool = False) -> np.ndarray:
@@ -264,6 +362,9 @@ class ResidentPoints:
 
     def __init__(self, curve: str, points: np.ndarray):
         p = _as_u64(points)
+        words = 2 * CURVES[curve]["nlimbs_p"]
+        if p.ndim != 2 or p.shape[1] != words:
+            raise ValueError(f"points must have shape (n, {words}), got {p.shape}")
         self.curve, self.n = curve, p.shape[0]
         self.ptr = lib().zkb200_device_upload(p.ctypes.data, p.nbytes)
 
@@ -271,6 +372,8 @@ class ResidentPoints:
         """scalars: (n, 4) or (nmsm, n, 4) host array -> one result per MSM."""
         cv = CURVES[self.curve]
         s = _as_u64(scalars)
+        if s.shape[-1] != 4 or s.size % (self.n * 4) != 0:
+            raise ValueError(f"scalars must have shape (n, 4) or (nmsm, n, 4) with n = {self.n}, got {s.shape}")
         batch = s.reshape(-1, self.n, 4)
         mode = _OUT[out]
         res = np.zeros((batch.shape[0], _OUT_COORDS[mode] * cv["nlimbs_p"]), dtype=np.uint64)
@@ -302,7 +405,7 @@ def last_stats() -> dict:
     L = lib()
     L.zkb200_last_affine_levels.restype = ctypes.c_int
     return {"phase_ms": dict(zip(names, [float(x) for x in ms])), "window": c.value, "nwindows": w.value,
-            "insertions": ins.value, "affine_levels": int(L.zkb200_last_affine_levels())}
+            "insertions": ins.value, "affine_levels": int(L.zkb200_last_affine_levels()), "srs_hit": bool(L.zkb200_last_srs_hit())}
 
 
 def imad_peak(kind: int = 0, iters: int = 2000) -> float:

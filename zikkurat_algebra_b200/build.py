@@ -1,6 +1,6 @@
 """Build libzkmsm_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-Sixteen translation units compiled in parallel (the fully unrolled 12-limb field code is slow to compile),
+Seventeen translation units compiled in parallel (the fully unrolled 12-limb field code is slow to compile),
 then linked into zikkurat_algebra_b200/lib/libzkmsm_b200.so with a static CUDA runtime.
 """
 from __future__ import annotations
@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libzkmsm_b200.so")
-UNITS = ["zkmsm", "sort", "ntt", "gfft", "bn254_acc", "bn254_red", "bls12381_acc", "bls12381_red",
+UNITS = ["zkmsm", "sort", "ntt", "gfft", "selftest", "bn254_acc", "bn254_red", "bls12381_acc", "bls12381_red",
          "bn254g2_acc", "bn254g2_red", "bls12381g2_acc", "bls12381g2_red", "bn254_aff", "bls12381_aff", "bn254g2_aff", "bls12381g2_aff"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

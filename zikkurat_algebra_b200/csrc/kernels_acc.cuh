@@ -198,8 +198,8 @@ k_fixup_level(const uint32_t* __restrict__ keys_in, const XyzzMem<typename C::Fp
 // faster with 1, 8 limbs 10 % faster with 0 (profiles/r1_notes.md).  Override: $ZKB200_ACC_VARIANT.
 template <class C>
 inline int accumulate_variant() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ZKB200_ACC_VARIANT"); v = e ? atoi(e) : (C::Fp::L > 8 ? 1 : 0); }
+  // read once; initialisation of a function-local static is thread-safe (one host thread per device may get here)
+  static const int v = [] { const char* e = getenv("ZKB200_ACC_VARIANT"); return e ? atoi(e) : (C::Fp::L > 8 ? 1 : 0); }();
   return v;
 }
 

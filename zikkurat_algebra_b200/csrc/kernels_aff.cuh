@@ -17,6 +17,12 @@
 // k_accumulate / fix-up path; runs that were closed inside a block were already written to their buckets.
 // P+P, P+(-P) and infinity operands are classified per merge and keep their exact group-law meaning.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "aff_plan.cuh"
 #include "kernels_acc.cuh"
 #include "msm_common.cuh"
@@ -558,6 +564,35 @@ void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t*
       keys, vals, points, tmp_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
 }
 
+// ---- host helpers -------------------------------------------------------------------------------------------------
+#define ZK_AFF_CK(x)                                                                                            \
+  do {                                                                                                          \
+    cudaError_t e__ = (x);                                                                                      \
+    if (e__ != cudaSuccess) {                                                                                   \
+      fprintf(stderr, "[zkmsm_b200] fatal: %s failed at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      abort();                                                                                                  \
+    }                                                                                                           \
+  } while (0)
+// The opt-in for more than 48 KB of dynamic shared memory is a per-device function attribute: set it ONCE per kernel
+// instantiation and device (bit mask), not before every launch.
+template <class K>
+inline void aff_allow_smem(K kernel, size_t smem) {
+  static std::mutex mu;                                            // K is the same function TYPE for all instantiations with
+  static std::vector<std::pair<const void*, unsigned>> seen;      // one signature, so the mask is keyed by the function pointer
+  int dev = 0;
+  ZK_AFF_CK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& e : seen)
+    if (e.first == (const void*)kernel) {
+      if (e.second & (1u << dev)) return;
+      ZK_AFF_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      e.second |= 1u << dev;
+      return;
+    }
+  ZK_AFF_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  seen.emplace_back((const void*)kernel, 1u << dev);
+}
+
 // ---- host driver: R levels over sorted pairs, then the records ------------------------------------------------------
 template <class C>
 int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int R,
@@ -565,8 +600,8 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
                        XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
   using P = typename C::Fp;
   int launches = 0;
-  int inl = -1;   // code shape of the additions: multiplications inlined (1) or out of line (0); $ZKB200_AFF_INLINE
-  if (inl < 0) { const char* e = getenv("ZKB200_AFF_INLINE"); inl = e ? atoi(e) : (P::L > 8 ? 0 : 1); }
+  // code shape of the additions: multiplications inlined (1) or out of line (0); $ZKB200_AFF_INLINE
+  static const int inl = [] { const char* e = getenv("ZKB200_AFF_INLINE"); return e ? atoi(e) : (P::L > 8 ? 0 : 1); }();
   const size_t smem = aff_stage_bytes<P>();
   const int G = ln.n;
   const cudaStream_t* big = ln.big;
@@ -593,8 +628,7 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
   size_t lvl_off[2] = {tmp_base[0], tmp_base[1]};   // where the current level's sums start in the temporary array
   // merges per thread: AFF_B (measured: fewer merges per thread = more threads = more inversion-chain work, a loss
   // even for small levels); $ZKB200_AFF_B overrides, down to AFF_B_MIN
-  static int forced_B = -1;
-  if (forced_B < 0) { const char* e = getenv("ZKB200_AFF_B"); forced_B = e ? atoi(e) : 0; }
+  static const int forced_B = [] { const char* e = getenv("ZKB200_AFF_B"); return e ? atoi(e) : 0; }();
   auto pick_B = [&](uint32_t) -> int {
     if (forced_B > 0) return forced_B > AFF_B ? AFF_B : (forced_B < AFF_B_MIN ? AFF_B_MIN : forced_B);
     return AFF_B;
@@ -614,9 +648,9 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot, B);
     else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot, B);
     launches++;
-    if (big[g] != chain[g]) { cudaEventRecord(ln.ev_a[g], big[g]); cudaStreamWaitEvent(chain[g], ln.ev_a[g], 0); }
+    if (big[g] != chain[g]) { ZK_AFF_CK(cudaEventRecord(ln.ev_a[g], big[g])); ZK_AFF_CK(cudaStreamWaitEvent(chain[g], ln.ev_a[g], 0)); }
     launches += batch_invert<P>(chain[g], tot, T0, tot + T0 * P::L, &inv[g]);
-    if (big[g] != chain[g]) { cudaEventRecord(ln.ev_c[g], chain[g]); cudaStreamWaitEvent(big[g], ln.ev_c[g], 0); }
+    if (big[g] != chain[g]) { ZK_AFF_CK(cudaEventRecord(ln.ev_c[g], chain[g])); ZK_AFF_CK(cudaStreamWaitEvent(big[g], ln.ev_c[g], 0)); }
   };
   // step 3 of level r for group g
   auto do_add = [&](int g, int r) {
@@ -636,11 +670,11 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
 #define ZK_AFF_ADD(L0, LA)                                                                                                    \
   do {                                                                                                                        \
     if (inl) {                                                                                                                \
-      cudaFuncSetAttribute(k_aff_add<C, L0, LA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+      aff_allow_smem(k_aff_add<C, L0, LA, false>, smem);                                                                      \
       k_aff_add<C, L0, LA, false><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off, \
                                                                          pre, inv[g], st_out, ko, vo, NB, bg, B);             \
     } else {                                                                                                                  \
-      cudaFuncSetAttribute(k_aff_add<C, L0, LA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+      aff_allow_smem(k_aff_add<C, L0, LA, true>, smem);                                                                       \
       k_aff_add<C, L0, LA, true><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off,  \
                                                                         pre, inv[g], st_out, ko, vo, NB, bg, B);              \
     }                                                                                                                         \

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include "msm_common.cuh"
 #include "gfft.cuh"
 #include "ntt.cuh"
+#include "selftest.cuh"
 #include "sort.cuh"
 
 using namespace zk;
@@ -46,6 +48,7 @@ struct Stats {
   float ms[9] = {0};
   int c = 0, W = 0, slices = 1, aff_levels = 0;
   bool have_phases = false;
+  bool srs_hit = false;        // the point array came from the resident-copy cache (no points crossed PCIe)
   bool slice_ran[8] = {false};
   long long insertions = 0;
 };
@@ -80,15 +83,52 @@ struct DeviceCtx {
   bool stage_used[STAGE_SLOTS] = {false};
   std::mutex mu;              // one MSM at a time per device (workspaces are shared)
   Stats stats;
+  int resident[4] = {0, 0, 0, 0};   // resident k_accumulate threads of this device, per curve id (filled under mu)
+  struct StagePool* pool = nullptr; // persistent staging threads for pageable sources (created on first use)
+  // Device-resident copies of point arrays the caller keeps passing (the SRS of a KZG prover), see srs_lookup
+  struct SrsEntry { const void* host; size_t bytes; uint64_t fp; int curve; void* dev; uint64_t last_use; };
+  std::vector<SrsEntry> srs;
+  size_t srs_bytes = 0;
+  uint64_t srs_clock = 0;
 
+  void srs_drop_all() {
+    for (auto& e : srs) CK(cudaFree(e.dev));
+    srs.clear();
+    srs_bytes = 0;
+  }
   void* ensure(int which, size_t bytes) {
     if (bytes > cap[which]) {
       if (buf[which]) CK(cudaFree(buf[which]));
+      buf[which] = nullptr;
+      cap[which] = 0;
       size_t want = bytes + bytes / 8 + 256;
-      CK(cudaMalloc(&buf[which], want));
+      cudaError_t e = cudaMalloc(&buf[which], want);
+      if (e == cudaErrorMemoryAllocation) {
+        // out of device memory: give back what is only a cache (resident point arrays), then ask for the exact size
+        (void)cudaGetLastError();
+        srs_drop_all();
+        want = bytes + 256;
+        e = cudaMalloc(&buf[which], want);
+      }
+      if (e != cudaSuccess) {
+        size_t fr = 0, tot = 0;
+        (void)cudaMemGetInfo(&fr, &tot);
+        fprintf(stderr, "[zkmsm_b200] fatal: device %d cannot provide a %zu-byte workspace (%zu of %zu bytes free): %s\n", dev, want,
+                fr, tot, cudaGetErrorString(e));
+        abort();
+      }
       cap[which] = want;
     }
     return buf[which];
+  }
+  void release_workspaces() {   // under mu
+    for (int i = 0; i < B_COUNT; i++) {
+      if (buf[i]) CK(cudaFree(buf[i]));
+      buf[i] = nullptr;
+      cap[i] = 0;
+    }
+    srs_drop_all();
+    if (h_out) { CK(cudaFreeHost(h_out)); h_out = nullptr; h_out_cap = 0; }
   }
   uint32_t* ensure_host(size_t bytes) {
     if (bytes > h_out_cap) {
@@ -105,13 +145,18 @@ std::mutex g_init_mu;
 std::atomic<int> g_device{-1};
 std::atomic<long long> g_launches{0};  // kernels launched by this library since load
 
+std::vector<int> device_list();
+
+// The ONE place that decides which GPU a call without an explicit device runs on: zkb200_set_device, else a
+// one-element device list (zkb200_set_devices / $ZKB200_DEVICES="2"), else $ZKB200_DEVICE, else 0.  Uploads
+// (zkb200_device_upload), statistics and MSM calls therefore always agree.
 int current_device_choice() {
   int d = g_device.load();
   if (d >= 0) return d;
+  std::vector<int> devs = device_list();
+  if (devs.size() == 1) return devs[0];
   const char* e = getenv("ZKB200_DEVICE");
-  d = e ? atoi(e) : 0;
-  g_device.store(d);
-  return d;
+  return e ? atoi(e) : 0;
 }
 
 DeviceCtx& get_ctx(int d = -1) {
@@ -191,38 +236,139 @@ bool host_is_pinned(const void* p) {
   return false;
 }
 
+// Persistent staging threads (created on the first pageable copy of a device, never joined: they sleep on a condition
+// variable between copies).  A job = one host_to_device call; worker w stages chunks w, w+T, ... into its ring slots.
+struct StagePool {
+  static constexpr int T = 4;            // STAGE_SLOTS is a multiple of T: a slot is always reused by the same thread
+  std::mutex m;
+  std::condition_variable cv_work, cv_done;
+  uint64_t gen = 0;
+  int pending = 0;
+  DeviceCtx* cx = nullptr;
+  uint8_t* dst = nullptr;
+  const uint8_t* src = nullptr;
+  size_t bytes = 0;
+  cudaStream_t stream = nullptr;
+
+  explicit StagePool(DeviceCtx* c) : cx(c) {
+    for (int w = 0; w < T; w++) std::thread([this, w] { worker(w); }).detach();
+  }
+  void worker(int w) {
+    if (cudaSetDevice(cx->dev) != cudaSuccess) abort();
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv_work.wait(lk, [&] { return gen != seen; });
+        seen = gen;
+      }
+      constexpr int R = DeviceCtx::STAGE_SLOTS;
+      constexpr size_t CH = DeviceCtx::STAGE_BYTES;
+      const size_t nchunks = (bytes + CH - 1) / CH;
+      for (size_t i = w; i < nchunks; i += T) {
+        const int slot = (int)(i % R);
+        if (cx->stage_used[slot]) CK(cudaEventSynchronize(cx->stage_ev[slot]));   // previous DMA out of this slot finished
+        const size_t off = i * CH, len = bytes - off < CH ? bytes - off : CH;
+        memcpy(cx->stage + (size_t)slot * CH, src + off, len);
+        CK(cudaMemcpyAsync(dst + off, cx->stage + (size_t)slot * CH, len, cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(cx->stage_ev[slot], stream));
+        cx->stage_used[slot] = true;
+      }
+      {
+        std::lock_guard<std::mutex> lk(m);
+        if (--pending == 0) cv_done.notify_one();
+      }
+    }
+  }
+  void copy(uint8_t* d, const uint8_t* s, size_t n, cudaStream_t st) {   // returns when every chunk has been queued
+    std::unique_lock<std::mutex> lk(m);
+    dst = d; src = s; bytes = n; stream = st;
+    pending = T;
+    gen++;
+    cv_work.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+};
+
 void host_to_device(DeviceCtx& cx, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
   if (bytes == 0) return;
   const bool pinned = host_is_pinned(src);
-  if (pinned || bytes < ((size_t)2 << 20) || getenv("ZKB200_NO_STAGING")) {
+  static const bool no_staging = getenv("ZKB200_NO_STAGING") != nullptr;
+  if (pinned || bytes < ((size_t)2 << 20) || no_staging) {
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     return;
   }
-  constexpr int R = DeviceCtx::STAGE_SLOTS;
-  constexpr size_t CH = DeviceCtx::STAGE_BYTES;
   if (!cx.stage) {
-    CK(cudaMallocHost((void**)&cx.stage, R * CH));
-    for (int i = 0; i < R; i++) CK(cudaEventCreateWithFlags(&cx.stage_ev[i], cudaEventDisableTiming));
+    CK(cudaMallocHost((void**)&cx.stage, DeviceCtx::STAGE_SLOTS * DeviceCtx::STAGE_BYTES));
+    for (int i = 0; i < DeviceCtx::STAGE_SLOTS; i++) CK(cudaEventCreateWithFlags(&cx.stage_ev[i], cudaEventDisableTiming));
   }
-  const size_t nchunks = (bytes + CH - 1) / CH;
-  const int T = 4;                       // R is a multiple of T: a slot is always reused by the same thread
-  const int dev = cx.dev;
-  std::vector<std::thread> th;
-  for (int w = 0; w < T; w++) {
-    th.emplace_back([&, w] {
-      if (cudaSetDevice(dev) != cudaSuccess) abort();
-      for (size_t i = w; i < nchunks; i += T) {
-        const int slot = (int)(i % R);
-        if (cx.stage_used[slot]) CK(cudaEventSynchronize(cx.stage_ev[slot]));   // previous DMA out of this slot finished
-        const size_t off = i * CH, len = bytes - off < CH ? bytes - off : CH;
-        memcpy(cx.stage + (size_t)slot * CH, (const uint8_t*)src + off, len);
-        CK(cudaMemcpyAsync((uint8_t*)dst + off, cx.stage + (size_t)slot * CH, len, cudaMemcpyHostToDevice, stream));
-        CK(cudaEventRecord(cx.stage_ev[slot], stream));
-        cx.stage_used[slot] = true;
-      }
-    });
+  if (!cx.pool) cx.pool = new StagePool(&cx);
+  cx.pool->copy((uint8_t*)dst, (const uint8_t*)src, bytes, stream);
+}
+
+// ---- resident point arrays ("SRS cache") --------------------------------------------------------------------------------
+// The reference's callers commit again and again over ONE point array (examples/KZG.hs:77-88,110-116: every commitPoly /
+// openingProof is `msm coeffs tauG1s`), and points are 2/3..3/4 of the input bytes.  A host point array is therefore kept
+// on the device after its first use, keyed by (host pointer, byte count, curve) and guarded by a 64-bit fingerprint of
+// a strided sample of its words (first and last 256 bytes in full): a later call with the same key and fingerprint uses
+// the resident copy and moves only the scalars.  A different fingerprint under the same key (the allocator handed the
+// address to another array) replaces the entry.  Least recently used entries go when the budget
+// ($ZKB200_SRS_CACHE_MB, default 16384; 0 disables the cache) is exceeded or when a workspace allocation fails.
+// Contract: the fingerprint samples ~1500 words, so a caller that rewrites a FEW points of an array in place between
+// calls must disable the cache or use a fresh buffer (the reference's FlatArrays are immutable: Class/Flat.hs:81-90).
+size_t srs_budget_bytes() {
+  static const size_t b = [] {
+    const char* e = getenv("ZKB200_SRS_CACHE_MB");
+    return (size_t)(e ? atoll(e) : 16384) << 20;
+  }();
+  return b;
+}
+uint64_t srs_fingerprint(const void* p, size_t bytes) {
+  const uint64_t* w = (const uint64_t*)p;
+  const size_t nw = bytes / 8;
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+  auto mix = [&](uint64_t v) { h = (h ^ v) * 0x100000001B3ull; h ^= h >> 29; };
+  const size_t edge = nw < 32 ? nw : 32;
+  for (size_t i = 0; i < edge; i++) { mix(w[i]); mix(w[nw - 1 - i]); }
+  const size_t S = 1024;
+  if (nw > 64)
+    for (size_t i = 0; i < S; i++) mix(w[(size_t)(((unsigned __int128)i * nw) / S)]);
+  return h;
+}
+// under cx.mu.  Returns the resident copy or nullptr; *fp_out receives the fingerprint for srs_insert.
+const uint32_t* srs_lookup(DeviceCtx& cx, int curve, const void* host, size_t bytes, uint64_t* fp_out) {
+  if (srs_budget_bytes() == 0 || bytes < ((size_t)64 << 10) || bytes > srs_budget_bytes()) return nullptr;
+  const uint64_t fp = srs_fingerprint(host, bytes);
+  *fp_out = fp;
+  for (size_t i = 0; i < cx.srs.size(); i++) {
+    auto& e = cx.srs[i];
+    if (e.host == host && e.bytes == bytes && e.curve == curve) {
+      if (e.fp == fp) { e.last_use = ++cx.srs_clock; return (const uint32_t*)e.dev; }
+      CK(cudaFree(e.dev));                       // same address, other content: stale
+      cx.srs_bytes -= e.bytes;
+      cx.srs.erase(cx.srs.begin() + i);
+      return nullptr;
+    }
   }
-  for (auto& t : th) t.join();
+  return nullptr;
+}
+// under cx.mu, after a call that uploaded `bytes` of points to d_src (device): keep a copy.  Failure to allocate is
+// not an error (the cache is an optimisation).
+void srs_insert(DeviceCtx& cx, int curve, const void* host, size_t bytes, uint64_t fp, const void* d_src, cudaStream_t s) {
+  if (srs_budget_bytes() == 0 || bytes < ((size_t)64 << 10) || bytes > srs_budget_bytes()) return;
+  while (cx.srs_bytes + bytes > srs_budget_bytes() && !cx.srs.empty()) {
+    size_t lru = 0;
+    for (size_t i = 1; i < cx.srs.size(); i++) if (cx.srs[i].last_use < cx.srs[lru].last_use) lru = i;
+    CK(cudaFree(cx.srs[lru].dev));
+    cx.srs_bytes -= cx.srs[lru].bytes;
+    cx.srs.erase(cx.srs.begin() + lru);
+  }
+  void* d = nullptr;
+  if (cudaMalloc(&d, bytes) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  CK(cudaMemcpyAsync(d, d_src, bytes, cudaMemcpyDeviceToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  cx.srs.push_back({host, bytes, fp, curve, d, ++cx.srs_clock});
+  cx.srs_bytes += bytes;
 }
 
 struct DeviceGuard {  // run on our device, then give the caller its own current device back
@@ -233,6 +379,12 @@ struct DeviceGuard {  // run on our device, then give the caller its own current
   }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+template <class C> struct CurveId;
+template <> struct CurveId<Bn254> { static constexpr int value = ZKB200_BN128; };
+template <> struct CurveId<Bls12381> { static constexpr int value = ZKB200_BLS12_381; };
+template <> struct CurveId<Bn254G2> { static constexpr int value = ZKB200_BN128_G2; };
+template <> struct CurveId<Bls12381G2> { static constexpr int value = ZKB200_BLS12_381_G2; };
 
 // curves whose affine pre-reduction kernels are built (kernels_aff.cuh; <curve>_aff.cu)
 template <class C> struct HasAffineTree { static constexpr bool value = false; };
@@ -264,7 +416,7 @@ int pick_window(size_t n, int nmsm, int nbits) {
 
 template <class C>
 void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc,
-             int nl, int mont, int out_mode, int window, uint64_t* out) {
+             int nl, int mont, int out_mode, int window, uint64_t* out, int out_loc = ZKB200_HOST) {
   using P = typename C::Fp;
   constexpr int L = P::L;
   using Mem = XyzzMem<P>;
@@ -296,11 +448,28 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       for (int m0 = 0; m0 < nmsm; m0 += sub) {
         int cntm = nmsm - m0 < sub ? nmsm - m0 : sub;
         run_msm<C>(cx, cntm, n, scalars + (size_t)m0 * n * nl, sloc, points, ploc, nl, mont, out_mode, c,
-                   out + (size_t)m0 * out_c * (L / 2));
+                   out + (size_t)m0 * out_c * (L / 2), out_loc);
       }
       return;
     }
     const uint32_t NB = 1u << (c - 1);
+    if (nmsm > 1) {
+      // Batches are bounded by memory as well as by the grid limit: pairs (ping-pong keys + values) cost 16 bytes per
+      // insertion, buckets and chunk heads about two XYZZ records per bucket.  A batch that would not fit in what is
+      // free (plus the workspaces this device already holds) is processed in halves instead of aborting in cudaMalloc.
+      size_t fr = 0, tot = 0, held = 0;
+      CK(cudaMemGetInfo(&fr, &tot));
+      for (int i = 0; i < B_COUNT; i++) held += cx.cap[i];
+      const double need = (double)nmsm * W * ((double)n * 16.0 + (double)NB * 2.5 * sizeof(Mem)) + (double)nmsm * n * nl * 8.0;
+      if (need > 0.8 * (double)(fr + held)) {
+        const int half = nmsm / 2;
+        const int out_c = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
+        run_msm<C>(cx, half, n, scalars, sloc, points, ploc, nl, mont, out_mode, c, out, out_loc);
+        run_msm<C>(cx, nmsm - half, n, scalars + (size_t)half * n * nl, sloc, points, ploc, nl, mont, out_mode, c,
+                   out + (size_t)half * out_c * (L / 2), out_loc);
+        return;
+      }
+    }
     const int nseg = nmsm * W;
     st.c = c; st.W = W; st.insertions = (long long)nseg * (long long)n;
 
@@ -354,7 +523,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     const size_t slice_stride = (size_t)nseg * NB;   // buckets per slice
     Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)K * slice_stride * sizeof(Mem));
     CK(cudaMemsetAsync(buckets, 0, (size_t)K * slice_stride * sizeof(Mem), s));  // ZZ = 0: every bucket starts at infinity
-    static int resident = 0;   // one per curve (template instantiation)
+    int& resident = cx.resident[CurveId<C>::value];   // per device and curve (cx.mu is held)
     if (resident == 0) resident = accumulate_resident_threads<C>();
     // Sorted pairs per thread: every accumulate grid is a whole number of waves of resident threads so that
     // all SMs drain together; about 48 insertions per thread for small problems (several waves), up to 192
@@ -691,12 +860,20 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     }
     st.have_phases = true;
   }
-  CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
+  if (out_loc == ZKB200_DEVICE) {
+    // result records stay on the device (multi-GPU combine without a host bounce): device-to-device, record by record
+    for (int m = 0; m < nmsm; m++)
+      CK(cudaMemcpyAsync((uint32_t*)out + (size_t)m * out_coords * L, d_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4,
+                         cudaMemcpyDeviceToDevice, s));
+  } else {
+    CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaEventRecord(cx.ev[8], s));
   CK(cudaStreamSynchronize(s));
   CK(cudaStreamSynchronize(cx.s_copy));
-  for (int m = 0; m < nmsm; m++)
-    memcpy((uint32_t*)out + (size_t)m * out_coords * L, h_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4);
+  if (out_loc != ZKB200_DEVICE)
+    for (int m = 0; m < nmsm; m++)
+      memcpy((uint32_t*)out + (size_t)m * out_coords * L, h_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4);
   if (st.have_phases) {
     // phase times summed over the slices (CUDA events on the launching stream)
     const int map[5][3] = {{3, 5, 1}, {5, 4, 2}, {4, 0, 3}, {0, 1, 4}, {1, 2, 5}};  // {from, to, stats slot}
@@ -751,15 +928,28 @@ std::vector<int> device_list() {
 
 template <class C>
 void run_on(int dev, int nmsm, size_t n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc, int nl, int mont,
-            int out_mode, int window, uint64_t* out) {
+            int out_mode, int window, uint64_t* out, int out_loc = ZKB200_HOST) {
   DeviceCtx& cx = get_ctx(dev);
   DeviceGuard guard(cx.dev);
   std::lock_guard<std::mutex> lk(cx.mu);
-  run_msm<C>(cx, nmsm, n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out);
+  if (ploc == ZKB200_HOST && n > 0) {
+    const size_t bytes = n * (size_t)(2 * C::Fp::L) * 4;
+    uint64_t fp = 0;
+    const uint32_t* resident = srs_lookup(cx, CurveId<C>::value, points, bytes, &fp);
+    if (resident) {
+      run_msm<C>(cx, nmsm, n, scalars, sloc, (const uint64_t*)resident, ZKB200_DEVICE, nl, mont, out_mode, window, out, out_loc);
+      cx.stats.srs_hit = true;
+      return;
+    }
+    run_msm<C>(cx, nmsm, n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out, out_loc);
+    if (fp) srs_insert(cx, CurveId<C>::value, points, bytes, fp, cx.buf[B_POINTS], cx.s_main);   // the upload is still there
+    return;
+  }
+  run_msm<C>(cx, nmsm, n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out, out_loc);
 }
 
 template <class C>
-void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out);
+void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out, int in_loc = ZKB200_HOST);
 
 // Sharded execution over several devices (host buffers only).
 //  * one MSM: contiguous slices of both vectors, one XYZZ partial per device, summed on the first device
@@ -799,11 +989,27 @@ void run_multi(const std::vector<int>& devs, int nmsm, size_t n, const uint64_t*
 }
 
 void msm_entry(int curve, int nmsm, long n, const uint64_t* scalars, int sloc, const uint64_t* points, int ploc, int nl,
-               int mont, int out_mode, int window, uint64_t* out) {
+               int mont, int out_mode, int window, uint64_t* out, int out_loc = ZKB200_HOST) {
   if (n < 0) n = 0;
   if (curve < 0 || curve > ZKB200_BLS12_381_G2) { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
   std::vector<int> devs = device_list();
-  const bool multi = devs.size() > 1 && sloc == ZKB200_HOST && ploc == ZKB200_HOST && nmsm >= 1 &&
+  if (n > 0) {
+    // a device pointer must live on the GPU the call runs on (no peer access is set up): fail with a message, not a fault
+    const int exec_dev = current_device_choice();
+    const void* dp[3] = {sloc == ZKB200_DEVICE ? scalars : nullptr, ploc == ZKB200_DEVICE ? points : nullptr,
+                         out_loc == ZKB200_DEVICE ? out : nullptr};
+    for (const void* q : dp) {
+      if (!q) continue;
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, q) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) || attr.device != exec_dev) {
+        (void)cudaGetLastError();
+        fprintf(stderr, "[zkmsm_b200] fatal: a pointer passed as device memory is not device memory of GPU %d (the device this "
+                        "call runs on: zkb200_set_device / $ZKB200_DEVICE / a one-element device list)\n", exec_dev);
+        abort();
+      }
+    }
+  }
+  const bool multi = devs.size() > 1 && sloc == ZKB200_HOST && ploc == ZKB200_HOST && out_loc == ZKB200_HOST && nmsm >= 1 &&
                      ((nmsm == 1 && (size_t)n >= ((size_t)1 << 16) * devs.size()) || (nmsm >= (int)devs.size()));
   if (multi) {
     switch (curve) {
@@ -814,17 +1020,17 @@ void msm_entry(int curve, int nmsm, long n, const uint64_t* scalars, int sloc, c
     }
     return;
   }
-  int dev = devs.size() == 1 ? devs[0] : -1;
+  const int dev = -1;   // current_device_choice()
   switch (curve) {
-    case ZKB200_BN128: run_on<Bn254>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
-    case ZKB200_BLS12_381: run_on<Bls12381>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
-    case ZKB200_BN128_G2: run_on<Bn254G2>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
-    default: run_on<Bls12381G2>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out); break;
+    case ZKB200_BN128: run_on<Bn254>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out, out_loc); break;
+    case ZKB200_BLS12_381: run_on<Bls12381>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out, out_loc); break;
+    case ZKB200_BN128_G2: run_on<Bn254G2>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out, out_loc); break;
+    default: run_on<Bls12381G2>(dev, nmsm, (size_t)n, scalars, sloc, points, ploc, nl, mont, out_mode, window, out, out_loc); break;
   }
 }
 
 template <class C>
-void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out) {
+void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out, int in_loc) {
   constexpr int L = C::Fp::L;
   const int in_coords = in_mode == OUT_XYZZ ? 4 : 3;
   const int out_coords = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
@@ -832,7 +1038,8 @@ void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode
   uint32_t* d_in = (uint32_t*)cx.ensure(B_SCALARS, in_bytes);
   uint32_t* d_out = (uint32_t*)cx.ensure(B_OUT, 4 * L * 4);
   uint32_t* h_out = cx.ensure_host(4 * L * 4);
-  if (k > 0) CK(cudaMemcpyAsync(d_in, in, (size_t)k * in_coords * L * 4, cudaMemcpyHostToDevice, cx.s_main));
+  if (k > 0 && in_loc == ZKB200_DEVICE) d_in = (uint32_t*)in;   // partial points already on this device (NCCL all-gather output)
+  else if (k > 0) CK(cudaMemcpyAsync(d_in, in, (size_t)k * in_coords * L * 4, cudaMemcpyHostToDevice, cx.s_main));
   g_launches++;
   launch_sum_points<C>(cx.s_main, d_in, k, in_mode, out_mode, d_out);
   CK(cudaGetLastError());
@@ -842,20 +1049,26 @@ void run_sum(DeviceCtx& cx, int k, const uint64_t* in, int in_mode, int out_mode
 }
 
 // ---- IMAD throughput probe ------------------------------------------------------------------------
+// Register-resident products with a DIFFERENT multiplier per repetition (bb[r], advanced every iteration): with one
+// shared multiplier ptxas keeps a*b and turns the repeated mad.wide into 64-bit additions, which is what made the
+// round-1 "mad.wide" figure look 1.7x faster than the carry chains (tools/imad_forms.cu documents the forms and the SASS).
 template <int KIND>
 __global__ void __launch_bounds__(256) k_imad_probe(uint32_t* out, int iters) {
   uint32_t a[8], E[8], O[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) { a[i] = threadIdx.x * 2654435761u + i * 40503u + 1u; E[i] = a[i] ^ 0x9e3779b9u; O[i] = a[i] + i; }
   uint32_t b = blockIdx.x + 12345u;
+  uint32_t bb[4] = {b, b * 3u + 1u, b * 5u + 2u, b * 7u + 3u};
   if (KIND == 0) {
     for (int it = 0; it < iters; it++) {
 #pragma unroll
       for (int r = 0; r < 4; r++) {  // 4 x (two independent 4-product carry chains) = 32 products
-        cmad_row<8, false>(E, a, b);
-        cmad_row<8, false>(O, a, b ^ 0x55u);
+        cmad_row<8, false>(E, a, bb[r]);
+        cmad_row<8, false>(O, a, bb[r] ^ 0x55u);
       }
       b += E[0];
+#pragma unroll
+      for (int q = 0; q < 4; q++) bb[q] += b;
     }
   } else if (KIND == 1) {
     unsigned long long acc[8];
@@ -865,18 +1078,34 @@ __global__ void __launch_bounds__(256) k_imad_probe(uint32_t* out, int iters) {
 #pragma unroll
       for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[i]), "r"(b));
+        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[i]), "r"(bb[r]));
       b += (uint32_t)acc[0];
+#pragma unroll
+      for (int q = 0; q < 4; q++) bb[q] += b;
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) { E[i] = (uint32_t)acc[i]; O[i] = (uint32_t)(acc[i] >> 32); }
+  } else if (KIND == 3) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 8; i++)   // product only, folded in by one 3-input logic op on the other pipe
+          asm volatile("{ .reg .u64 t; .reg .u32 lo, hi; mul.wide.u32 t, %1, %2; mov.b64 {lo, hi}, t; lop3.b32 %0, %0, lo, hi, 0x96; }"
+                       : "+r"(E[i]) : "r"(a[i]), "r"(bb[r]));
+      b += E[0];
+#pragma unroll
+      for (int q = 0; q < 4; q++) bb[q] += b;
+    }
   } else {
     for (int it = 0; it < iters; it++) {
 #pragma unroll
       for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(E[i]) : "r"(a[i]), "r"(b));
+        for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(E[i]) : "r"(a[i]), "r"(bb[r]));
       b += E[0];
+#pragma unroll
+      for (int q = 0; q < 4; q++) bb[q] += b;
     }
   }
   uint32_t x = b;
@@ -989,15 +1218,24 @@ void zkb200_msm(int curve, int nmsm, long npoints, const uint64_t* scalars, int 
   msm_entry(curve, nmsm, npoints, scalars, scalars_loc, points, points_loc, expo_nlimbs, mont_coeff, out_mode, window, out);
 }
 
-void zkb200_sum_points(int curve, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out) {
+void zkb200_msm_ex(int curve, int nmsm, long npoints, const uint64_t* scalars, int scalars_loc, const uint64_t* points,
+                   int points_loc, int expo_nlimbs, int mont_coeff, int out_mode, int window, uint64_t* out, int out_loc) {
+  msm_entry(curve, nmsm, npoints, scalars, scalars_loc, points, points_loc, expo_nlimbs, mont_coeff, out_mode, window, out, out_loc);
+}
+
+void zkb200_sum_points_ex(int curve, int k, const uint64_t* in, int in_loc, int in_mode, int out_mode, uint64_t* out) {
   DeviceCtx& cx = get_ctx();
   DeviceGuard guard(cx.dev);
   std::lock_guard<std::mutex> lk(cx.mu);
-  if (curve == ZKB200_BN128) run_sum<Bn254>(cx, k, in, in_mode, out_mode, out);
-  else if (curve == ZKB200_BLS12_381) run_sum<Bls12381>(cx, k, in, in_mode, out_mode, out);
-  else if (curve == ZKB200_BN128_G2) run_sum<Bn254G2>(cx, k, in, in_mode, out_mode, out);
-  else if (curve == ZKB200_BLS12_381_G2) run_sum<Bls12381G2>(cx, k, in, in_mode, out_mode, out);
+  if (curve == ZKB200_BN128) run_sum<Bn254>(cx, k, in, in_mode, out_mode, out, in_loc);
+  else if (curve == ZKB200_BLS12_381) run_sum<Bls12381>(cx, k, in, in_mode, out_mode, out, in_loc);
+  else if (curve == ZKB200_BN128_G2) run_sum<Bn254G2>(cx, k, in, in_mode, out_mode, out, in_loc);
+  else if (curve == ZKB200_BLS12_381_G2) run_sum<Bls12381G2>(cx, k, in, in_mode, out_mode, out, in_loc);
   else { fprintf(stderr, "[zkmsm_b200] fatal: unknown curve id %d\n", curve); abort(); }
+}
+
+void zkb200_sum_points(int curve, int k, const uint64_t* in, int in_mode, int out_mode, uint64_t* out) {
+  zkb200_sum_points_ex(curve, k, in, ZKB200_HOST, in_mode, out_mode, out);
 }
 
 void zkb200_set_device(int device) { g_device.store(device); }
@@ -1028,6 +1266,90 @@ void zkb200_device_free(void* device_ptr) {
   DeviceGuard guard(cx.dev);
   std::lock_guard<std::mutex> lk(cx.mu);
   CK(cudaFree(device_ptr));
+}
+
+void zkb200_release_workspaces(void) {
+  for (int d = 0; d < MAX_DEV; d++) {
+    DeviceCtx& cx = g_ctx[d];
+    if (!cx.ready) continue;
+    DeviceGuard guard(cx.dev);
+    std::lock_guard<std::mutex> lk(cx.mu);
+    cx.release_workspaces();
+  }
+}
+
+void zkb200_srs_cache_drop(void) {
+  for (int d = 0; d < MAX_DEV; d++) {
+    DeviceCtx& cx = g_ctx[d];
+    if (!cx.ready) continue;
+    DeviceGuard guard(cx.dev);
+    std::lock_guard<std::mutex> lk(cx.mu);
+    cx.srs_drop_all();
+  }
+}
+
+int zkb200_last_srs_hit(void) {
+  DeviceCtx& cx = get_ctx();
+  std::lock_guard<std::mutex> lk(cx.mu);
+  return cx.stats.srs_hit ? 1 : 0;
+}
+
+// Element-wise self-tests of the device primitives (selftest.cu): host arrays in, host array out, temporary device
+// buffers (not the MSM workspaces).  field: 0 = bn128 Fp, 1 = bls12_381 Fp, 2 = bn128 Fr, 3 = bls12_381 Fr.
+void zkb200_selftest_field(int field, int op, long n, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d,
+                           uint64_t* out) {
+  if (n <= 0) return;
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  const int L = (field == 1) ? 12 : 8;
+  const size_t bytes = (size_t)n * L * 4;
+  const uint64_t* in[4] = {a, b, c, d};
+  uint32_t* din[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t* dout = nullptr;
+  cudaStream_t s = cx.s_main;
+  for (int k = 0; k < 4; k++)
+    if (in[k]) { CK(cudaMalloc((void**)&din[k], bytes)); CK(cudaMemcpyAsync(din[k], in[k], bytes, cudaMemcpyHostToDevice, s)); }
+  CK(cudaMalloc((void**)&dout, bytes));
+  g_launches++;
+  switch (field) {
+    case 0: launch_selftest_field<Bn254Fp>(s, op, (size_t)n, din[0], din[1], din[2], din[3], dout); break;
+    case 1: launch_selftest_field<Bls12381Fp>(s, op, (size_t)n, din[0], din[1], din[2], din[3], dout); break;
+    case 2: launch_selftest_field<Bn254Fr>(s, op, (size_t)n, din[0], din[1], din[2], din[3], dout); break;
+    case 3: launch_selftest_field<Bls12381Fr>(s, op, (size_t)n, din[0], din[1], din[2], din[3], dout); break;
+    default: fprintf(stderr, "[zkmsm_b200] fatal: unknown field id %d\n", field); abort();
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int k = 0; k < 4; k++) if (din[k]) CK(cudaFree(din[k]));
+  CK(cudaFree(dout));
+}
+
+void zkb200_selftest_group(int curve, int op, long n, const uint64_t* p1, const uint64_t* z1, const uint64_t* p2, const uint64_t* z2,
+                           uint64_t* out_affine) {
+  if (n <= 0) return;
+  if (curve != ZKB200_BN128 && curve != ZKB200_BLS12_381) { fprintf(stderr, "[zkmsm_b200] fatal: selftest_group: G1 curves only\n"); abort(); }
+  DeviceCtx& cx = get_ctx();
+  DeviceGuard guard(cx.dev);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  const int L = curve == ZKB200_BLS12_381 ? 12 : 8;
+  const size_t fb = (size_t)n * L * 4;
+  uint32_t *dp1, *dz1, *dp2, *dz2, *dout;
+  cudaStream_t s = cx.s_main;
+  CK(cudaMalloc((void**)&dp1, 2 * fb)); CK(cudaMalloc((void**)&dp2, 2 * fb)); CK(cudaMalloc((void**)&dout, 2 * fb));
+  CK(cudaMalloc((void**)&dz1, fb)); CK(cudaMalloc((void**)&dz2, fb));
+  CK(cudaMemcpyAsync(dp1, p1, 2 * fb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dp2, p2, 2 * fb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dz1, z1, fb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dz2, z2, fb, cudaMemcpyHostToDevice, s));
+  g_launches++;
+  if (curve == ZKB200_BN128) launch_selftest_group<Bn254>(s, op, (size_t)n, dp1, dz1, dp2, dz2, dout);
+  else launch_selftest_group<Bls12381>(s, op, (size_t)n, dp1, dz1, dp2, dz2, dout);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_affine, dout, 2 * fb, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaFree(dp1)); CK(cudaFree(dp2)); CK(cudaFree(dout)); CK(cudaFree(dz1)); CK(cudaFree(dz2));
 }
 
 void zkb200_ntt(int curve, int m, const uint64_t* gen, const uint64_t* src, int src_loc, uint64_t* tgt, int tgt_loc, int inverse) {
@@ -1078,6 +1400,7 @@ double zkb200_imad_peak(int kind, int iters) {
     CK(cudaEventRecord(cx.ev[0], s));
     if (kind == 0) k_imad_probe<0><<<blocks, 256, 0, s>>>(d, iters);
     else if (kind == 1) k_imad_probe<1><<<blocks, 256, 0, s>>>(d, iters);
+    else if (kind == 3) k_imad_probe<3><<<blocks, 256, 0, s>>>(d, iters);
     else k_imad_probe<2><<<blocks, 256, 0, s>>>(d, iters);
     CK(cudaGetLastError());
     CK(cudaEventRecord(cx.ev[1], s));
