@@ -543,3 +543,17 @@ static void msm_threads(const curve_t *C, long n, const uint64_t *e, const uint6
 
 DEFINE_CURVE(bn128, BN)
 DEFINE_CURVE(bls12_381, BLS)
+
+// ------------------------------------------------------------------------------------
+// Array drivers for element-wise differential tests (tests/test_device_primitives.py): apply ANY function with the
+// reference's element signatures -- in practice the unmodified reference's own <curve>_Fp_mont_mul & co. from
+// oracle/_ref, passed in as a function pointer -- to n consecutive operands in a C loop (10^6 ctypes calls from
+// Python would take longer than the GPU test budget allows).
+typedef void (*zko_fn2)(const uint64_t *, uint64_t *);
+typedef void (*zko_fn3)(const uint64_t *, const uint64_t *, uint64_t *);
+EXPORT void zko_map2(zko_fn2 f, long n, int in_limbs, int out_limbs, const uint64_t *a, uint64_t *out) {
+  for (long i = 0; i < n; i++) f(a + (size_t)i * in_limbs, out + (size_t)i * out_limbs);
+}
+EXPORT void zko_map3(zko_fn3 f, long n, int a_limbs, int b_limbs, int out_limbs, const uint64_t *a, const uint64_t *b, uint64_t *out) {
+  for (long i = 0; i < n; i++) f(a + (size_t)i * a_limbs, b + (size_t)i * b_limbs, out + (size_t)i * out_limbs);
+}

@@ -192,8 +192,8 @@ DeviceCtx& get_ctx(int d = -1) {
         }
         for (int g = 0; g < 8; g++) {
           CK(cudaStreamCreateWithPriority(&cx.pl.post[g], cudaStreamNonBlocking, hi_pri));
-          CK(cudaEventCreateWithFlags(&cx.pl.ev_fix[g], cudaEventDisableTiming));
-          CK(cudaEventCreateWithFlags(&cx.pl.ev_post[g], cudaEventDisableTiming));
+          CK(cudaEventCreate(&cx.pl.ev_fix[g]));    // timing enabled: the $ZKB200_TRACE timeline reads them
+          CK(cudaEventCreate(&cx.pl.ev_post[g]));
         }
         CK(cudaEventCreateWithFlags(&cx.pl.ev_sorted, cudaEventDisableTiming));
         for (int g = 0; g < 4; g++) {
@@ -431,6 +431,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
 
   const int nbits = mont ? C::Fr::BITS : 64 * nl;
   int c = 0, W = 0, K = 1;
+  int trace_groups = 0, trace_g0[9] = {0};
   CK(cudaEventRecord(cx.ev[0], s));
   if (n == 0) {
     g_launches++;
@@ -480,7 +481,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // the accumulation of slice k instead of in front of everything.  Costs one extra bucket addition per
     // bucket and slice in k_reduce_first.  (Adding into shared buckets inside k_accumulate was tried and
     // loses: the rare per-run addition diverges and is paid by the whole warp on almost every step.)
-    if (nmsm == 1 && sloc == ZKB200_HOST && ploc == ZKB200_HOST) {
+    if (nmsm == 1 && sloc == ZKB200_HOST) {   // points may already be resident (SRS cache): the scalars still travel
       const char* e = getenv("ZKB200_SLICES");
       K = e ? atoi(e) : (n >= ((size_t)1 << 19) ? 2 : 1);   // measured: 2 slices -4 % (2^20) .. -14 % (2^24) end to end
       if (K > MAX_SLICES) K = MAX_SLICES;
@@ -498,8 +499,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       // accumulate time of slice 0 must cover the PCIe time of slice 1: f >= t/(a+t) with a = accumulate and
       // t = transfer time per point (measured: BN254 ~1.9/1.9 us per 1000 points, BLS12-381 5.4/2.6, G2 heavier)
       // Ordinary (pageable) memory goes through the staging ring at about half the PCIe rate, so t doubles.
-      const bool pinned = host_is_pinned(points);
+      const bool pinned = host_is_pinned(ploc == ZKB200_HOST ? (const void*)points : (const void*)scalars);
       int pct = e ? atoi(e) : (pinned ? (L <= 8 ? 50 : 25) : (L <= 12 ? 50 : 35));   // measured (profiles/r1_notes.md)
+      if (!e && ploc != ZKB200_HOST) pct = 25;   // only 32 bytes per point travel: a short first slice hides the rest
       if (pct < 5) pct = 5;
       if (pct > 95) pct = 95;
       lo[1] = (n * (size_t)pct / 100) & ~(size_t)3;
@@ -618,6 +620,8 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         for (g = 1; g < NG; g++) if (grp0[g] <= grp0[g - 1]) grp0[g] = grp0[g - 1] + 1;
       }
     }
+    trace_groups = split_tail ? NG : 0;
+    for (int g = 0; g <= NG; g++) trace_g0[g] = grp0[g];
     const int conc_segs = stagger ? nseg : (nseg + NG - 1) / NG * nlanes;   // segments in flight at a time
     auto pick_chunk = [&](size_t per_seg) -> int {
       const char* e = getenv("ZKB200_CHUNK");
@@ -890,6 +894,25 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     CK(cudaEventElapsedTime(&st.ms[7], cx.ev[6], cx.ev[8]));
   }
   CK(cudaEventElapsedTime(&st.ms[8], cx.ev[0], cx.ev[8]));
+  static const bool trace = getenv("ZKB200_TRACE") != nullptr;
+  if (trace && st.have_phases) {
+    // timeline of the window groups (ms since the start of the call): when a group's buckets were complete (its lane
+    // finished the fix-up) and when its bucket reduction + share of the window combination were done
+    float t_sorted = 0, t_lanes = 0, t_post = 0;
+    CK(cudaEventElapsedTime(&t_sorted, cx.ev[0], cx.gev[4]));
+    CK(cudaEventElapsedTime(&t_lanes, cx.ev[0], cx.ev[5]));
+    CK(cudaEventElapsedTime(&t_post, cx.ev[0], cx.ev[6]));
+    fprintf(stderr, "[zkmsm_b200 trace] n=%zu c=%d W=%d R=%d sorted %.3f lanes_done %.3f post_done %.3f total %.3f |", n, c, W,
+            st.aff_levels, t_sorted, t_lanes, t_post, st.ms[8]);
+    if (trace_groups > 1)
+      for (int g = trace_groups - 1; g >= 0; g--) {
+        float a = 0, b = 0;
+        if (cudaEventElapsedTime(&a, cx.ev[0], cx.pl.ev_fix[g]) == cudaSuccess && cudaEventElapsedTime(&b, cx.ev[0], cx.pl.ev_post[g]) == cudaSuccess)
+          fprintf(stderr, " g%d[%d,%d) buckets %.3f post %.3f |", g, trace_g0[g], trace_g0[g + 1], a, b);
+        else (void)cudaGetLastError();
+      }
+    fprintf(stderr, "\n");
+  }
   cx.stats = st;
 }
 
