@@ -630,7 +630,7 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
   // even for small levels); $ZKB200_AFF_B overrides, down to AFF_B_MIN
   static const int forced_B = [] { const char* e = getenv("ZKB200_AFF_B"); return e ? atoi(e) : 0; }();
   auto pick_B = [&](uint32_t) -> int {
-    if (forced_B > 0) return forced_B > AFF_B ? AFF_B : (forced_B < AFF_B_MIN ? AFF_B_MIN : forced_B);
+    if (forced_B > 0) return forced_B > 128 ? 128 : (forced_B < AFF_B_MIN ? AFF_B_MIN : forced_B);
     return AFF_B;
   };
   uint32_t* inv[2] = {nullptr, nullptr};

@@ -36,8 +36,10 @@ __device__ __forceinline__ void xyzz_dbl_tm(const Team& tm, Xyzz<P>& a) {
 }
 
 // ---- K5: bucket reduction  sum_b (b+1) * B[b]  by levels ------------------------------------------------
-// Invariant after every level:  R_seg = sum_t ( U[t] + M * t * V[t] ),  t = 0..S-1.
-// Level 1 reads the buckets (U = V = B, M = 1, weights t+1) with the classic running sum over m buckets.
+// Invariant after every level:  R_seg = sum_t ( U[t] + t * Vs[t] ),  t = 0..S-1, where Vs[t] is the plain sum of the
+// entry's buckets ALREADY multiplied by the entry's index stride (Vs = M * V): a level then needs only log2(m)
+// doublings of its V output, whatever its height, instead of log2(M) doublings of the weighted sum.
+// Level 1 reads the buckets (weights t+1) with the classic running sum over m buckets.
 // With K input slices (H2D overlap, see run_msm) there are K bucket arrays `slice_stride` apart; their
 // sum is taken on the fly: run += B_0[i] + ... + B_{K-1}[i] through the same addition site.
 // 12-limb fields: out-of-line multiplications (250 -> ~170 registers, 3 CTAs per SM); 8 limbs: inlined
@@ -57,18 +59,45 @@ k_reduce_first(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices,
     acc = RF_ADD(acc, run);
   }
   store_xyzz<P>(U + t, acc);
+#pragma unroll 1
+  for (int d = 0; d < log_m; d++) xyzz_dbl_nc<P>(run);     // Vs = m * V
   store_xyzz<P>(V + t, run);
 }
+// The same level with one 4-lane TEAM per output entry: ~3.5x shorter dependent chain per addition.  Used for the
+// window group that finishes last, where the latency of the chain is what the caller waits for; the single-thread
+// version above has the better throughput (the upper groups' reductions run under other groups' accumulation).
+template <class C>
+__global__ void __launch_bounds__(128)
+k_reduce_first_team(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices, size_t slice_stride, size_t total_out,
+                    int log_m, XyzzMem<typename C::Fp>* __restrict__ U, XyzzMem<typename C::Fp>* __restrict__ V) {
+  using P = typename C::Fp;
+  size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  if (t >= total_out) return;
+  const Team tm;
+  const XyzzMem<P>* b = buckets + (t << log_m);
+  Xyzz<P> run = xyzz_inf<P>(), acc = xyzz_inf<P>();
+  for (int i = (1 << log_m) - 1; i >= 0; i--) {
+#pragma unroll 1
+    for (int k = 0; k < nslices; k++) xyzz_add_tm<P>(tm, run, load_xyzz<P>(b + (size_t)k * slice_stride + i));
+    xyzz_add_tm<P>(tm, acc, run);
+  }
+#pragma unroll 1
+  for (int d = 0; d < log_m; d++) xyzz_dbl_tm<P>(tm, run);  // Vs = m * V
+  if (tm.t == 0) { store_xyzz<P>(U + t, acc); store_xyzz<P>(V + t, run); }
+}
 // Next levels: groups of m entries (t = g*m + i):
-//   U'[g] = sum_i U[t] + M * sum_i i*V[t],   V'[g] = sum_i V[t],   M' = M*m,   M = 2^log_M.
+//   U'[g] = sum_i U[t] + sum_i i*Vs[t],   Vs'[g] = m * sum_i Vs[t].
 // One task (= one output entry) is worked on by 16 lanes = 4 teams of 4 lanes.  Three teams run the three
-// chains of the level concurrently -- team 0: run += V_i, team 1: acc += run (one step behind, the run
+// chains of the level concurrently -- team 0: run += Vs_i, team 1: acc += run (one step behind, the run
 // values are handed over through shared memory), team 2: usum += U_i -- so a level is m + 1 dependent
-// additions deep instead of 3m, and the single inlined addition keeps operands in registers.
+// additions deep instead of 3m, and the single inlined addition keeps operands in registers.  At the end team 0
+// doubles its sum log2(m) times (the next level's Vs) while team 2 adds team 1's weighted sum to usum.
+// `levels` > 1: the same CTA-resident tasks repeat the step on their own outputs (only when ONE block holds a whole
+// segment's entries: the upper, tiny levels of the tree without a relaunch) -- see launch_reduce_next.
 template <class C>
 __global__ void __launch_bounds__(128)
 k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typename C::Fp>* __restrict__ Vin,
-              size_t total_out, int log_m, int log_M, XyzzMem<typename C::Fp>* __restrict__ Uout,
+              size_t total_out, int log_m, XyzzMem<typename C::Fp>* __restrict__ Uout,
               XyzzMem<typename C::Fp>* __restrict__ Vout) {
   using P = typename C::Fp;
   __shared__ XyzzMem<P> hand[128 / 16][2];   // per task: double-buffered hand-over slot
@@ -91,16 +120,16 @@ k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typ
       else if (q == 1) { if (s >= 1) B = load_xyzz<P>(&slot[(s - 1) & 1]); }
       else if (q == 2) B = load_xyzz<P>(u + i);
     } else {
-      // last step: team 1 scales its sum by M = 2^log_M and hands it to team 2, which adds it to usum
-      if (q == 1) {
-#pragma unroll 1
-        for (int d = 0; d < log_M; d++) X = xyzz_dbl_team<P>(tm, X);
-        if (tm.t == 0) store_xyzz<P>(&slot[0], X);
-      }
+      // last step: team 1 hands its weighted sum to team 2, which adds it to usum; team 0 scales its plain sum by m
+      if (q == 1 && tm.t == 0) store_xyzz<P>(&slot[0], X);
       __syncwarp(gmask);
       if (q == 2) B = load_xyzz<P>(&slot[0]);
     }
-    X = xyzz_add_team<P>(tm, X, B);                       // the only addition site; B = infinity is a no-op
+    if (s < m || q == 2) X = xyzz_add_team<P>(tm, X, B);  // the only addition site; B = infinity is a no-op
+    if (s == m && q == 0) {
+#pragma unroll 1
+      for (int d = 0; d < log_m; d++) X = xyzz_dbl_team<P>(tm, X);
+    }
     if (s < m && q == 0 && tm.t == 0) store_xyzz<P>(&slot[s & 1], X);
     __syncwarp(gmask);
   }
@@ -309,13 +338,18 @@ void launch_gen_chain(cudaStream_t s, const uint32_t* p0d, unsigned long long st
 
 template <class C>
 void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, int nslices, size_t slice_stride, size_t total_out,
-                         int log_m, XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V) {
-  k_reduce_first<C><<<(unsigned)((total_out + 127) / 128), 128, 0, s>>>(buckets, nslices, slice_stride, total_out, log_m, U, V);
+                         int log_m, XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V, int team) {
+  // 64-thread blocks: these launches run on high-priority side streams WHILE the accumulation kernels of other window
+  // groups own the SMs (3 CTAs of ~19.5 K registers each); a block is scheduled as soon as ONE of those CTAs retires only
+  // if its registers fit into that hole -- 128 threads x 255 registers never did, so the "overlapped" reductions used to
+  // wait until the accumulation queue ran dry.
+  if (team) k_reduce_first_team<C><<<(unsigned)((total_out * 4 + 63) / 64), 64, 0, s>>>(buckets, nslices, slice_stride, total_out, log_m, U, V);
+  else k_reduce_first<C><<<(unsigned)((total_out + 63) / 64), 64, 0, s>>>(buckets, nslices, slice_stride, total_out, log_m, U, V);
 }
 template <class C>
 void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin, size_t total_out,
-                        int log_m, int log_M, XyzzMem<typename C::Fp>* Uout, XyzzMem<typename C::Fp>* Vout) {
-  k_reduce_next<C><<<(unsigned)((total_out * 16 + 127) / 128), 128, 0, s>>>(Uin, Vin, total_out, log_m, log_M, Uout, Vout);
+                        int log_m, XyzzMem<typename C::Fp>* Uout, XyzzMem<typename C::Fp>* Vout) {
+  k_reduce_next<C><<<(unsigned)((total_out * 16 + 63) / 64), 64, 0, s>>>(Uin, Vin, total_out, log_m, Uout, Vout);
 }
 template <class C>
 void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out) {
@@ -332,8 +366,8 @@ void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, i
 
 #define ZK_INSTANTIATE_RED(C)                                                                                             \
   template void launch_reduce_first<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, size_t, size_t, int, XyzzMem<C::Fp>*,     \
-                                       XyzzMem<C::Fp>*);                                                                  \
-  template void launch_reduce_next<C>(cudaStream_t, const XyzzMem<C::Fp>*, const XyzzMem<C::Fp>*, size_t, int, int,        \
+                                       XyzzMem<C::Fp>*, int);                                                             \
+  template void launch_reduce_next<C>(cudaStream_t, const XyzzMem<C::Fp>*, const XyzzMem<C::Fp>*, size_t, int,             \
                                       XyzzMem<C::Fp>*, XyzzMem<C::Fp>*);                                                   \
   template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*);                        \
   template void launch_sum_points<C>(cudaStream_t, const uint32_t*, int, int, int, uint32_t*);                             \

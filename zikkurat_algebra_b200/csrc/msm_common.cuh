@@ -164,9 +164,10 @@ template <class C> void launch_fixup_level(cudaStream_t s, const uint32_t* keys_
                                            uint32_t T_in, uint32_t* keys_out, XyzzMem<typename C::Fp>* heads_out, uint32_t T_out,
                                            int nseg, uint32_t NB, XyzzMem<typename C::Fp>* buckets, int last);
 template <class C> void launch_reduce_first(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, int nslices, size_t slice_stride,
-                                            size_t total_out, int log_m, XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V);
+                                            size_t total_out, int log_m, XyzzMem<typename C::Fp>* U, XyzzMem<typename C::Fp>* V,
+                                            int team);
 template <class C> void launch_reduce_next(cudaStream_t s, const XyzzMem<typename C::Fp>* Uin, const XyzzMem<typename C::Fp>* Vin,
-                                           size_t total_out, int log_m, int log_M, XyzzMem<typename C::Fp>* Uout,
+                                           size_t total_out, int log_m, XyzzMem<typename C::Fp>* Uout,
                                            XyzzMem<typename C::Fp>* Vout);
 template <class C> void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out);
 template <class C> void launch_tail_group(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int Wg, int c, int extra,

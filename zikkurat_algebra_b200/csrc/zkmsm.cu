@@ -481,7 +481,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // the accumulation of slice k instead of in front of everything.  Costs one extra bucket addition per
     // bucket and slice in k_reduce_first.  (Adding into shared buckets inside k_accumulate was tried and
     // loses: the rare per-run addition diverges and is paid by the whole warp on almost every step.)
-    if (nmsm == 1 && sloc == ZKB200_HOST) {   // points may already be resident (SRS cache): the scalars still travel
+    // (only when the points travel too: with resident points -- SRS cache -- the 32 bytes per scalar are not worth the
+    //  smaller kernels of two slices: measured 8.5 -> 9.4 ms pageable, 7.7 -> 8.5 ms pinned at BLS12-381 2^20)
+    if (nmsm == 1 && sloc == ZKB200_HOST && ploc == ZKB200_HOST) {
       const char* e = getenv("ZKB200_SLICES");
       K = e ? atoi(e) : (n >= ((size_t)1 << 19) ? 2 : 1);   // measured: 2 slices -4 % (2^20) .. -14 % (2^24) end to end
       if (K > MAX_SLICES) K = MAX_SLICES;
@@ -499,9 +501,8 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       // accumulate time of slice 0 must cover the PCIe time of slice 1: f >= t/(a+t) with a = accumulate and
       // t = transfer time per point (measured: BN254 ~1.9/1.9 us per 1000 points, BLS12-381 5.4/2.6, G2 heavier)
       // Ordinary (pageable) memory goes through the staging ring at about half the PCIe rate, so t doubles.
-      const bool pinned = host_is_pinned(ploc == ZKB200_HOST ? (const void*)points : (const void*)scalars);
+      const bool pinned = host_is_pinned(points);
       int pct = e ? atoi(e) : (pinned ? (L <= 8 ? 50 : 25) : (L <= 12 ? 50 : 35));   // measured (profiles/r1_notes.md)
-      if (!e && ploc != ZKB200_HOST) pct = 25;   // only 32 bytes per point travel: a short first slice hides the rest
       if (pct < 5) pct = 5;
       if (pct > 95) pct = 95;
       lo[1] = (n * (size_t)pct / 100) & ~(size_t)3;
@@ -582,6 +583,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (stagger) NG = stagger;
     }
     const bool split_tail = NG > 1;
+    static const bool reduce_team = [] { const char* e = getenv("ZKB200_REDUCE_TEAM"); return e ? atoi(e) != 0 : true; }();
     int nlanes = 1;
     {
       const char* e = getenv("ZKB200_AFF_GROUPS");
@@ -675,7 +677,11 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (log_m1 > 5) log_m1 = 5;
       if (log_m1 > c - 1) log_m1 = c - 1;
     }
-    const size_t red_out = (size_t)nseg << (c - 1 - log_m1);
+    // The window group that finishes last (the bottom one) uses the team version of the first reduction level with a
+    // short chain (4 buckets per task); the output arrays are spaced for the smaller of the two group sizes.
+    const int log_mt = c - 1 < 2 ? c - 1 : 2;
+    const int log_mmin = log_mt < log_m1 ? log_mt : log_m1;
+    const size_t red_out = (size_t)nseg << (c - 1 - log_mmin);
     Mem* Ub[2] = {(Mem*)cx.ensure(B_U0, red_out * sizeof(Mem)), (Mem*)cx.ensure(B_U1, red_out * sizeof(Mem))};
     Mem* Vb[2] = {(Mem*)cx.ensure(B_V0, red_out * sizeof(Mem)), (Mem*)cx.ensure(B_V1, red_out * sizeof(Mem))};
     Mem* partials = (Mem*)cx.ensure(B_PARTIALS, 16 * sizeof(Mem));
@@ -787,22 +793,23 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
             cudaStream_t sp = cx.pl.post[gl[l]];
             CK(cudaEventRecord(cx.pl.ev_fix[gl[l]], sl));
             CK(cudaStreamWaitEvent(sp, cx.pl.ev_fix[gl[l]], 0));
-            const size_t ubase = (size_t)s0 << (c - 1 - log_m1);
+            const size_t ubase = (size_t)s0 << (c - 1 - log_mmin);
+            const bool team = gl[l] == 0 && reduce_team;   // the bottom group is the one the caller ends up waiting for
+            const int lm1 = team ? log_mt : log_m1;
             int logS = c - 1;
-            size_t total_out = (size_t)ns << (logS - log_m1);
+            size_t total_out = (size_t)ns << (logS - lm1);
             g_launches++;
-            launch_reduce_first<C>(sp, buckets + (size_t)s0 * NB, K, slice_stride, total_out, log_m1, Ub[0] + ubase, Vb[0] + ubase);
+            launch_reduce_first<C>(sp, buckets + (size_t)s0 * NB, K, slice_stride, total_out, lm1, Ub[0] + ubase, Vb[0] + ubase, team);
             CK(cudaGetLastError());
-            logS -= log_m1;
-            int log_M = log_m1, lv = 0;
+            logS -= lm1;
+            int lv = 0;
             while (logS > 0) {
               int lm = logS > 3 ? 3 : logS;
               total_out = (size_t)ns << (logS - lm);
               g_launches++;
-              launch_reduce_next<C>(sp, Ub[lv] + ubase, Vb[lv] + ubase, total_out, lm, log_M, Ub[lv ^ 1] + ubase, Vb[lv ^ 1] + ubase);
+              launch_reduce_next<C>(sp, Ub[lv] + ubase, Vb[lv] + ubase, total_out, lm, Ub[lv ^ 1] + ubase, Vb[lv ^ 1] + ubase);
               CK(cudaGetLastError());
               logS -= lm;
-              log_M += lm;
               lv ^= 1;
             }
             g_launches++;
@@ -842,18 +849,17 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       int logS = c - 1;
       size_t total_out = (size_t)nseg << (logS - log_m1);
       g_launches++;
-      launch_reduce_first<C>(s, buckets, K, slice_stride, total_out, log_m1, Ub[0], Vb[0]);
+      launch_reduce_first<C>(s, buckets, K, slice_stride, total_out, log_m1, Ub[0], Vb[0], 0);
       CK(cudaGetLastError());
       logS -= log_m1;
-      int log_M = log_m1, lv = 0;
+      int lv = 0;
       while (logS > 0) {
         int lm = logS > 3 ? 3 : logS;
         total_out = (size_t)nseg << (logS - lm);
         g_launches++;
-        launch_reduce_next<C>(s, Ub[lv], Vb[lv], total_out, lm, log_M, Ub[lv ^ 1], Vb[lv ^ 1]);
+        launch_reduce_next<C>(s, Ub[lv], Vb[lv], total_out, lm, Ub[lv ^ 1], Vb[lv ^ 1]);
         CK(cudaGetLastError());
         logS -= lm;
-        log_M += lm;
         lv ^= 1;
       }
       CK(cudaEventRecord(cx.ev[6], s));
