@@ -336,9 +336,11 @@ def main():
 
     def make_host_step(sc, pts):
         def step():
-            if inlib or (world == 1 and not batch):
+            if (inlib or world == 1) and not batch:
                 # exactly the call the reference's FFI makes
                 return zk.call_reference_symbol(entry_point(cfg), sc, pts, npoints=n)
+            if inlib:
+                return zk.msm_batch(curve, sc, pts, mont=mont, out="affine", window=args.window)
             if batch:
                 return msm_batch_dealt(curve, sc, pts, n, nmsm, mont=mont, resident=False, window=args.window)
             return msm_sharded(curve, sc, pts, npoints=n, mont=mont, resident=False, window=args.window)

@@ -8,6 +8,7 @@
 #include "ec.cuh"
 #include "recode.cuh"
 #include "aff_plan.cuh"
+#include "glv.cuh"
 #include <vector>
 
 using namespace zk;
@@ -183,3 +184,18 @@ extern "C" void he_recode(const uint64_t* scalar, int nbits, int c, int nwin, ui
   }
   keys[nwin] = carry;  // must be 0 when nwin*c >= nbits+1
 }
+
+// GLV split of one scalar (8 x 32-bit limbs in, any value < 2^256): out = |k1| (2 words), |k2| (2 words), flags[0..1] = signs;
+// and phi(x) = beta * x on a Montgomery coordinate
+#define DEFINE_GLV(NAME, C)                                                                                       \
+  extern "C" void he_##NAME##_glv_split(const uint64_t* k, uint64_t* k1, uint64_t* k2, int* flags) {              \
+    uint32_t kl[8], a[4], b[4];                                                                                   \
+    memcpy(kl, k, 32);                                                                                            \
+    bool n1, n2;                                                                                                  \
+    glv_decompose<GlvOf<C>::type>(kl, a, n1, b, n2);                                                              \
+    memcpy(k1, a, 16); memcpy(k2, b, 16);                                                                         \
+    flags[0] = n1; flags[1] = n2; }                                                                               \
+  extern "C" void he_##NAME##_glv_beta_x(const uint64_t* x, uint64_t* t) {                                        \
+    st<C::Fp>(t, glv_beta_x<C::Fp, GlvOf<C>::type>(ld<C::Fp>(x))); }
+DEFINE_GLV(bn128, Bn254)
+DEFINE_GLV(bls12_381, Bls12381)

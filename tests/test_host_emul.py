@@ -21,7 +21,7 @@ CURVES = ["bn128", "bls12_381"]
 
 @pytest.fixture(scope="module")
 def he():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("hd.cuh", "fp.cuh", "ec.cuh", "recode.cuh", "curve_params.cuh", "aff_plan.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("hd.cuh", "fp.cuh", "ec.cuh", "recode.cuh", "curve_params.cuh", "aff_plan.cuh", "glv.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", f"-I{CSRC}", SRC, "-o", SO], check=True)
     return ctypes.CDLL(SO)
@@ -281,3 +281,60 @@ def test_affine_tree_bookkeeping_and_arithmetic(he, curve):
                 got = out.tobytes()
                 for b in range(NB):
                     assert got[b * 16 * L:(b + 1) * 16 * L] == cv.affine_to_bytes(want[b]), (n, keys, R, b)
+
+
+def _cube_root_of_unity_pairs(cv):
+    """(beta, lambda) with phi(x, y) = (beta x, y) = [lambda](x, y) on G1, lambda the smaller root of x^2 + x + 1 mod r:
+    derived here from scratch (brute force over the two candidates each), independent of tools/gen_params.py"""
+    def roots(m):
+        # the two primitive cube roots of unity mod m: g^((m-1)/3) for a non-cube g
+        for g in range(2, 50):
+            w = pow(g, (m - 1) // 3, m)
+            if w != 1:
+                return [w, w * w % m]
+    lam = min(roots(cv.r))
+    for beta in roots(cv.p):
+        if cv.mul(lam, cv.gen) == (cv.gen[0] * beta % cv.p, cv.gen[1]):
+            return beta, lam
+    raise AssertionError("no matching beta")
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_glv_split_and_endomorphism(he, curve):
+    """glv.cuh: k = k1 + k2 lambda (mod r) with |k1|, |k2| < 2^127 for EVERY 256-bit k (std scalars are not reduced), and
+    x -> beta x is multiplication by lambda.  The reference lists the same (beta, lambda) pairs:
+    codegen/src/Zikkurat/CodeGen/Curve/Params.hs:162-165 (BN128), :200-203 (BLS12-381)."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    beta, lam = _cube_root_of_unity_pairs(cv)
+    ref_pairs = {"bn128": (2203960485148121921418603742825762020974279258880205651966,
+                           4407920970296243842393367215006156084916469457145843978461),
+                 "bls12_381": (4002409555221667392624310435006688643935503118305586438271171395842971157480381377015405980053539358417135540939436,
+                               228988810152649578064853576960394133503)}
+    assert (beta, lam) == ref_pairs[curve]
+    f = getattr(he, f"he_{curve}_glv_split")
+    f.argtypes = [refs.U64P, refs.U64P, refs.U64P, ctypes.POINTER(ctypes.c_int)]
+    f.restype = None
+    rng = random.Random(5)
+    r = cv.r
+    ks = [0, 1, 2, r - 1, r, r + 1, (1 << 256) - 1, 1 << 255, lam, lam - 1, lam + 1, r // 2, (1 << 253) - 1, (1 << 128), (1 << 127) - 1,
+          r - lam, 2 * r + 5, 5 * r - 1 if 5 * r < (1 << 256) else 2 * r - 1]
+    ks += [rng.randrange(1 << 256) for _ in range(3000)] + [rng.randrange(r) for _ in range(3000)]
+    ks += [rng.randrange(1 << b) for b in (64, 127, 128, 129, 192) for _ in range(200)]
+    worst = 0
+    for k in ks:
+        K = _arr(k.to_bytes(32, "little"))
+        k1, k2 = np.zeros(2, np.uint64), np.zeros(2, np.uint64)
+        fl = (ctypes.c_int * 2)()
+        f(refs.ptr(K), refs.ptr(k1), refs.ptr(k2), fl)
+        a = int.from_bytes(k1.tobytes(), "little") * (-1 if fl[0] else 1)
+        b = int.from_bytes(k2.tobytes(), "little") * (-1 if fl[1] else 1)
+        assert (a + b * lam - k) % r == 0, hex(k)
+        worst = max(worst, abs(a), abs(b))
+    assert worst < 1 << 127
+    # the endomorphism on Montgomery coordinates
+    for s in (1, 2, 0x1234567, r - 1):
+        P = cv.mul(s, cv.gen)
+        X = _arr(cv.fp_to_bytes(P[0]))
+        got = cv.fp_from_bytes(refs.call2(he, f"he_{curve}_glv_beta_x", X, L).tobytes())
+        assert (got, P[1]) == cv.mul(lam, P)

@@ -6,6 +6,7 @@
 #include "ec_team.cuh"
 #include <cstdlib>
 
+#include "glv.cuh"
 #include "msm_common.cuh"
 
 namespace zk {
@@ -40,6 +41,82 @@ k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int
     keys[o] = key;
     vals[o] = (uint32_t)i | (neg << 31);
   }
+}
+
+// The same with the GLV split (glv.cuh): every scalar becomes two 127-bit halves, k1 over P_i (pair position i of a
+// segment) and k2 over phi(P_i) (position n + i, point index n + i of the expanded array); segments hold 2n pairs.
+// The sign of a half flips the sign of its digits' points.
+template <class C>
+__global__ void __launch_bounds__(256)
+k_recode_glv(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int mont, int c, int W,
+             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  using G = typename GlvOf<C>::type;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * (size_t)nmsm) return;
+  size_t msm = gid / n, i = gid - msm * n;
+  Fe<typename C::Fr> k;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(scalars + gid * (size_t)nl64);
+  if (nl64 == 4) {
+    const uint4* q = reinterpret_cast<const uint4*>(src);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    k.l[0] = a.x; k.l[1] = a.y; k.l[2] = a.z; k.l[3] = a.w;
+    k.l[4] = b.x; k.l[5] = b.y; k.l[6] = b.z; k.l[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) k.l[j] = (j < 2 * nl64) ? src[j] : 0u;
+  }
+  if (mont) k = fe_from_mont<typename C::Fr>(k);
+  uint32_t h[2][8];
+  bool neg[2];
+#pragma unroll
+  for (int j = 4; j < 8; j++) h[0][j] = h[1][j] = 0;
+  glv_decompose<G>(k.l, h[0], neg[0], h[1], neg[1]);
+  const size_t n2 = 2 * n;
+  size_t seg0 = msm * (size_t)W;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    uint32_t carry = 0;
+    const uint32_t idx = (uint32_t)(half ? n + i : i);
+    for (int w = 0; w < W; w++) {
+      uint32_t key, dneg;
+      recode_digit(h[half], G::BITS, c, w, carry, key, dneg);
+      size_t o = (seg0 + w) * n2 + idx;
+      keys[o] = key;
+      vals[o] = idx | ((key != 0 && (dneg != 0) != neg[half]) ? 0x80000000u : 0u);
+    }
+  }
+}
+
+// [P_0 .. P_{n-1} ; phi(P_0) .. phi(P_{n-1})]: the expanded point array of the GLV split.  phi(x, y) = (beta x, y);
+// the point at infinity (all-0xFF record) stays what it is.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_glv_points(const uint32_t* __restrict__ src, size_t n, uint32_t* __restrict__ dst) {
+  using P = typename C::Fp;
+  using G = typename GlvOf<C>::type;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int PW = (2 * P::L) / 4;
+  const uint4* q = reinterpret_cast<const uint4*>(src + i * (2 * P::L));
+  uint4* d0 = reinterpret_cast<uint4*>(dst + i * (2 * P::L));
+  uint4* d1 = reinterpret_cast<uint4*>(dst + (n + i) * (2 * P::L));
+  uint32_t t[2 * P::L];
+#pragma unroll
+  for (int kq = 0; kq < PW; kq++) {
+    uint4 v = __ldg(q + kq);
+    d0[kq] = v;
+    t[4 * kq] = v.x; t[4 * kq + 1] = v.y; t[4 * kq + 2] = v.z; t[4 * kq + 3] = v.w;
+  }
+  Affine<P> p;
+#pragma unroll
+  for (int kq = 0; kq < P::L; kq++) { p.x.l[kq] = t[kq]; p.y.l[kq] = t[P::L + kq]; }
+  if (!affine_is_inf<P>(p)) {
+    Fe<P> bx = glv_beta_x<P, G>(p.x);
+#pragma unroll
+    for (int kq = 0; kq < P::L; kq++) t[kq] = bx.l[kq];
+  }
+#pragma unroll
+  for (int kq = 0; kq < PW; kq++) d1[kq] = make_uint4(t[4 * kq], t[4 * kq + 1], t[4 * kq + 2], t[4 * kq + 3]);
 }
 
 // ---- K4: bucket accumulation ---------------------------------------------------------------------------
@@ -210,6 +287,18 @@ void launch_recode(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, 
   k_recode<C><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(scalars, nl64, n, nmsm, mont, nbits, c, W, keys, vals);
 }
 template <class C>
+void launch_recode_glv(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int c, int W, uint32_t* keys,
+                       uint32_t* vals) {
+  if constexpr (GlvOf<C>::available) {
+    size_t tot = (size_t)nmsm * n;
+    k_recode_glv<C><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(scalars, nl64, n, nmsm, mont, c, W, keys, vals);
+  }
+}
+template <class C>
+void launch_glv_points(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst) {
+  if constexpr (GlvOf<C>::available) k_glv_points<C><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(src, n, dst);
+}
+template <class C>
 void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int nseg,
                        int chunk, uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets,
                        XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
@@ -248,6 +337,8 @@ void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<t
 #define ZK_INSTANTIATE_ACC(C)                                                                                              \
   template int accumulate_resident_threads<C>();                                                                          \
   template void launch_recode<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, int, uint32_t*, uint32_t*); \
+  template void launch_recode_glv<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, uint32_t*, uint32_t*);  \
+  template void launch_glv_points<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*);                                    \
   template void launch_accumulate<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,     \
                                      uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);                      \
   template void launch_fixup_level<C>(cudaStream_t, const uint32_t*, const XyzzMem<C::Fp>*, uint32_t, uint32_t*,           \

@@ -18,6 +18,7 @@
 #include "../../include/zk_msm_b200.h"
 #include "msm_common.cuh"
 #include "gfft.cuh"
+#include "glv.cuh"
 #include "ntt.cuh"
 #include "selftest.cuh"
 #include "sort.cuh"
@@ -39,7 +40,7 @@ namespace {
 enum Buf {
   B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
   B_U0, B_V0, B_U1, B_V1, B_OUT, B_NTT_TABLE, B_AFF_TMP, B_AFF_PRE, B_AFF_BINV, B_AFF_ST0, B_AFF_ST1, B_AFF_KEYS,
-  B_AFF_VALS, B_PARTIALS, B_COUNT
+  B_AFF_VALS, B_PARTIALS, B_GLV_POINTS, B_COUNT
 };
 constexpr int N_EV = 9;
 constexpr int MAX_DEV = 16;
@@ -429,7 +430,13 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   uint32_t* d_out = (uint32_t*)cx.ensure(B_OUT, (size_t)nmsm * 4 * L * 4);
   uint32_t* h_out = cx.ensure_host((size_t)nmsm * 4 * L * 4);
 
-  const int nbits = mont ? C::Fr::BITS : 64 * nl;
+  int nbits = mont ? C::Fr::BITS : 64 * nl;
+  // GLV split (glv.cuh): 2n points (P_i, phi(P_i)) with 127-bit scalars -> half the windows.  Only for scalars that are
+  // longer than the split halves in the first place ($ZKB200_GLV=0 switches it off).
+  static const bool glv_on = [] { const char* e = getenv("ZKB200_GLV"); return e ? atoi(e) != 0 : true; }();
+  const bool glv = GlvOf<C>::available && glv_on && nbits > 160 && n > 0;
+  const size_t F = glv ? 2 : 1;        // pairs per point and window
+  if (glv) nbits = 127;
   int c = 0, W = 0, K = 1;
   int trace_groups = 0, trace_g0[9] = {0};
   CK(cudaEventRecord(cx.ev[0], s));
@@ -438,7 +445,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     launch_tail<C>(s, nullptr, nmsm, 0, 0, out_mode, d_out);
     CK(cudaGetLastError());
   } else {
-    c = window > 0 ? window : pick_window(n, nmsm, nbits);
+    c = window > 0 ? window : pick_window(n * F, nmsm, nbits);
     if (c < 1) c = 1;
     if (c > 24) c = 24;
     W = signed_windows(nbits, c);
@@ -461,7 +468,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       size_t fr = 0, tot = 0, held = 0;
       CK(cudaMemGetInfo(&fr, &tot));
       for (int i = 0; i < B_COUNT; i++) held += cx.cap[i];
-      const double need = (double)nmsm * W * ((double)n * 16.0 + (double)NB * 2.5 * sizeof(Mem)) + (double)nmsm * n * nl * 8.0;
+      const double need = (double)nmsm * W * ((double)(n * F) * 16.0 + (double)NB * 2.5 * sizeof(Mem)) + (double)nmsm * n * nl * 8.0;
       if (need > 0.8 * (double)(fr + held)) {
         const int half = nmsm / 2;
         const int out_c = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
@@ -472,7 +479,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       }
     }
     const int nseg = nmsm * W;
-    st.c = c; st.W = W; st.insertions = (long long)nseg * (long long)n;
+    st.c = c; st.W = W; st.insertions = (long long)nseg * (long long)(n * F);
 
     // ---- point slices -----------------------------------------------------------------------------------
     // With host buffers the input vectors are cut into K contiguous slices that go through
@@ -509,18 +516,21 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     }
     lo[K] = n;
     for (int k = 0; k < K; k++) if (lo[k + 1] - lo[k] > nmax) nmax = lo[k + 1] - lo[k];
+    const size_t pmax = nmax * F;        // sorted pairs per segment of the longest slice
 
     // ---- inputs -> device: copy stream, queued slice by slice just before the work that needs them ----
     const uint64_t* d_scalars = scalars;
     const uint32_t* d_points = (const uint32_t*)points;
     if (sloc == ZKB200_HOST) d_scalars = (const uint64_t*)cx.ensure(B_SCALARS, (size_t)nmsm * n * nl * 8);
     if (ploc == ZKB200_HOST) d_points = (const uint32_t*)cx.ensure(B_POINTS, n * (size_t)(2 * L) * 4);
+    // GLV: slice k's points are expanded to [P ; phi(P)] (2 nk records) at record offset 2 lo[k] of this array
+    uint32_t* glv_points = glv ? (uint32_t*)cx.ensure(B_GLV_POINTS, 2 * n * (size_t)(2 * L) * 4) : nullptr;
 
     // ---- work arrays (sized for the longest slice) ----
-    const size_t pairs_max = (size_t)nseg * nmax;
+    const size_t pairs_max = (size_t)nseg * pmax;
     uint32_t* keys[2] = {(uint32_t*)cx.ensure(B_KEYS0, pairs_max * 4), (uint32_t*)cx.ensure(B_KEYS1, pairs_max * 4)};
     uint32_t* vals[2] = {(uint32_t*)cx.ensure(B_VALS0, pairs_max * 4), (uint32_t*)cx.ensure(B_VALS1, pairs_max * 4)};
-    const int tiles_max = (int)((nmax + SORT_TILE - 1) / SORT_TILE);
+    const int tiles_max = (int)((pmax + SORT_TILE - 1) / SORT_TILE);
     uint32_t* cnt = (uint32_t*)cx.ensure(B_CNT, (size_t)nseg * SORT_RADIX * tiles_max * 4);
     uint32_t* rowsum = (uint32_t*)cx.ensure(B_ROWSUM, (size_t)nseg * SORT_RADIX * 4);
     const size_t slice_stride = (size_t)nseg * NB;   // buckets per slice
@@ -539,20 +549,20 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       const char* e = getenv("ZKB200_AFFINE");
       if (e) {
         R = atoi(e);
-      } else if (L > 8 ? nmax >= ((size_t)1 << 19) : (nmax >= ((size_t)1 << 20) && nmax < ((size_t)1 << 22))) {
+      } else if (L > 8 ? nmax >= ((size_t)1 << 19) : (nmax >= ((size_t)1 << 20) && nmax < ((size_t)1 << 22))) {   // (points, not pairs)
         // 12 limbs: -7 % (2^19), -15 % (2^20), -22 % (2^21), -17 % (2^22, 2^24) of the whole MSM; 8 limbs: -7 % at 2^20,
         // -2 % at 2^21, nothing at 2^22 and a loss at 2^24 (the cheaper multiplication leaves the tree's extra
         // memory traffic exposed)
-        R = ilog2_floor(nmax / NB + 1) - 2;
+        R = ilog2_floor(pmax / NB + 1) - 2;
         if (pairs_max >= ((size_t)1 << 26) || L >= 16) R++;   // G2: heavier additions, one more level pays
         if (R > 5) R = 5;
       }
       if (R < 0) R = 0;
       if (R > 12) R = 12;
-      while (R > 0 && (nmax >> R) < 2) R--;
-      if (pairs_max >= ((size_t)1 << 30) || n >= ((size_t)1 << 30)) R = 0;   // 30-bit refs
+      while (R > 0 && (pmax >> R) < 2) R--;
+      if (pairs_max >= ((size_t)1 << 30) || n * F >= ((size_t)1 << 30)) R = 0;   // 30-bit refs
       if (R > 0) {   // workspace guard: temporary points + running products
-        AffSizes z = aff_sizes(nmax, nseg, R);
+        AffSizes z = aff_sizes(pmax, nseg, R);
         if ((z.tmp_points * 2 + z.pre_elems) * (size_t)L * 4 > ((size_t)48 << 30)) R = 0;
       }
     }
@@ -563,7 +573,8 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // lower groups.  Two lanes (streams) work on two groups at a time so that the latency-bound kernels of one lane
     // (inversion chains of the affine tree) run under the other lane's additions.
     int NG = 1;
-    if (nmsm == 1 && W >= 8) {
+    static const int min_split_w = [] { const char* e = getenv("ZKB200_MIN_SPLIT_W"); return e ? atoi(e) : 8; }();
+    if (nmsm == 1 && W >= min_split_w) {
       const char* e = getenv("ZKB200_WGROUPS");
       NG = e ? atoi(e) : 2;   // measured: 2 groups -1.3 % (BLS12-381 2^20) .. -2 % (2^22); 4 and 8 lose (smaller kernels)
       if (NG < 1) NG = 1;
@@ -575,7 +586,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     // Groups from the bottom: [0, 3W/16), [3W/16, 9W/16), [9W/16, W)  ($ZKB200_STAGGER = number of groups 2..4,
     // 0 = off; $ZKB200_STAGGER_SPLIT = the inner boundaries in windows).
     int stagger = 0;
-    if (nmsm == 1 && W >= 8 && R > 0) {
+    if (nmsm == 1 && W >= min_split_w && R > 0) {
       const char* e = getenv("ZKB200_STAGGER");
       stagger = e ? atoi(e) : 3;
       if (stagger < 2) stagger = 0;
@@ -641,13 +652,13 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (ch > 1024) ch = 1024;
       return (int)ch;
     };
-    const int chunk = pick_chunk(nmax);
+    const int chunk = pick_chunk(pmax);
     AffSizes az{};
     AffWork aw{};
     int chunk_rec = chunk;
     size_t binv_stride = 0;
     if (R > 0) {
-      az = aff_sizes(nmax, nseg, R);
+      az = aff_sizes(pmax, nseg, R);
       binv_stride = az.binv_elems + 64;
       aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)(2 * L) * 4);
       aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, az.pre_elems * (size_t)L * 4);
@@ -658,7 +669,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       aw.vals_out = (uint32_t*)cx.ensure(B_AFF_VALS, az.rec * 4 + 16);
       chunk_rec = pick_chunk(az.nrec);
     }
-    uint32_t cps_max = (uint32_t)((nmax + chunk - 1) / chunk);
+    uint32_t cps_max = (uint32_t)((pmax + chunk - 1) / chunk);
     if (R > 0) {
       uint32_t c2 = (uint32_t)((az.nrec + chunk_rec - 1) / chunk_rec);
       if (c2 > cps_max) cps_max = c2;
@@ -703,14 +714,20 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       }
       CK(cudaEventRecord(ge[3], s));
       g_launches++;
-      launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, keys[0], vals[0]);
+      const size_t pk = nk * F;          // pairs per segment of this slice
+      if constexpr (GlvOf<C>::available) {
+        if (glv) launch_recode_glv<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, c, W, keys[0], vals[0]);
+        else launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, keys[0], vals[0]);
+      } else {
+        launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, keys[0], vals[0]);
+      }
       CK(cudaGetLastError());
       CK(cudaEventRecord(ge[5], s));
-      const int tiles = (int)((nk + SORT_TILE - 1) / SORT_TILE);
+      const int tiles = (int)((pk + SORT_TILE - 1) / SORT_TILE);
       int cur = 0;
       for (int shift = 0; shift < c; shift += 8) {
         g_launches += 3;
-        sort_pass(s, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], nk, nseg, shift, cnt, rowsum, tiles);
+        sort_pass(s, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], pk, nseg, shift, cnt, rowsum, tiles);
         CK(cudaGetLastError());
         cur ^= 1;
       }
@@ -719,14 +736,25 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (ploc == ZKB200_HOST) {
         size_t off = lo[k] * (size_t)(2 * L), cnt32 = nk * (size_t)(2 * L);
         host_to_device(cx, (uint32_t*)d_points + off, (const uint32_t*)points + off, cnt32 * 4, cx.s_copy);
+      }
+      const uint32_t* pts_k = d_points + lo[k] * (size_t)(2 * L);
+      if constexpr (GlvOf<C>::available) {
+        if (glv) {   // on the copy stream: behind this slice's upload, under the recoding and the sort of the pairs
+          uint32_t* ext = glv_points + 2 * lo[k] * (size_t)(2 * L);
+          g_launches++;
+          launch_glv_points<C>(cx.s_copy, pts_k, nk, ext);
+          CK(cudaGetLastError());
+          pts_k = ext;
+        }
+      }
+      if (ploc == ZKB200_HOST || glv) {
         CK(cudaEventRecord(cx.ev_pt[k], cx.s_copy));
         CK(cudaStreamWaitEvent(s, cx.ev_pt[k], 0));
       }
       CK(cudaEventRecord(ge[0], s));
       Mem* kb_ = buckets + (size_t)k * slice_stride;
-      const uint32_t* pts_k = d_points + lo[k] * (size_t)(2 * L);
-      AffSizes zk_ = aff_sizes(nk, nseg, R > 0 ? R : 1);
-      const uint32_t cps = R > 0 ? (uint32_t)((zk_.nrec + chunk_rec - 1) / chunk_rec) : (uint32_t)((nk + chunk - 1) / chunk);
+      AffSizes zk_ = aff_sizes(pk, nseg, R > 0 ? R : 1);
+      const uint32_t cps = R > 0 ? (uint32_t)((zk_.nrec + chunk_rec - 1) / chunk_rec) : (uint32_t)((pk + chunk - 1) / chunk);
       const bool last_slice = k == K - 1;
       // Window groups, top windows first, two at a time on the two lanes.  A group's fix-up runs on its lane; after
       // the LAST slice its bucket reduction and its share of the window combination follow on a high-priority stream
@@ -761,14 +789,14 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         }
         if constexpr (HasAffineTree<C>::value) {
           if (R > 0)
-            g_launches += launch_affine_tree<C>(ln, keys[cur], vals[cur], pts_k, nk, R, NB, kb_, aw, chunk_rec, cps, heads, head_keys);
+            g_launches += launch_affine_tree<C>(ln, keys[cur], vals[cur], pts_k, pk, R, NB, kb_, aw, chunk_rec, cps, heads, head_keys);
         }
         for (int l = 0; l < ln.n; l++) {
           const int s0 = ln.seg0[l], ns = ln.segs[l];
           cudaStream_t sl = ln.big[l];
           if (R == 0) {
             g_launches++;
-            launch_accumulate<C>(sl, keys[cur] + (size_t)s0 * nk, vals[cur] + (size_t)s0 * nk, pts_k, nk, ns, chunk, cps, NB,
+            launch_accumulate<C>(sl, keys[cur] + (size_t)s0 * pk, vals[cur] + (size_t)s0 * pk, pts_k, pk, ns, chunk, cps, NB,
                                  kb_ + (size_t)s0 * NB, heads + (size_t)s0 * cps, head_keys + (size_t)s0 * cps);
           }
           CK(cudaGetLastError());
