@@ -77,8 +77,8 @@ struct DeviceCtx {
   uint32_t* h_out = nullptr;  // pinned staging for results
   size_t h_out_cap = 0;
   // pinned staging ring for pageable host inputs (see host_to_device)
-  static constexpr int STAGE_SLOTS = 8;
-  static constexpr size_t STAGE_BYTES = (size_t)4 << 20;
+  static constexpr int STAGE_SLOTS = 16;                 // two ring slots per staging thread (at most 8 threads)
+  static constexpr size_t STAGE_BYTES = (size_t)2 << 20;
   uint8_t* stage = nullptr;
   cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr};
   bool stage_used[STAGE_SLOTS] = {false};
@@ -240,7 +240,11 @@ bool host_is_pinned(const void* p) {
 // Persistent staging threads (created on the first pageable copy of a device, never joined: they sleep on a condition
 // variable between copies).  A job = one host_to_device call; worker w stages chunks w, w+T, ... into its ring slots.
 struct StagePool {
-  static constexpr int T = 4;            // STAGE_SLOTS is a multiple of T: a slot is always reused by the same thread
+  // Threads: the host cores this process can count on -- online cores / visible GPUs (one process per GPU is the usual
+  // multi-GPU arrangement, and 8 x 4 staging threads on a 32-core box fight each other) -- between 2 and 8
+  // ($ZKB200_STAGE_THREADS overrides).  A slot is always reused by the same thread: chunk i uses slot i % (2T) and
+  // belongs to thread i % T.
+  int T = 4;
   std::mutex m;
   std::condition_variable cv_work, cv_done;
   uint64_t gen = 0;
@@ -252,6 +256,17 @@ struct StagePool {
   cudaStream_t stream = nullptr;
 
   explicit StagePool(DeviceCtx* c) : cx(c) {
+    const char* e = getenv("ZKB200_STAGE_THREADS");
+    if (e && atoi(e) > 0) T = atoi(e);
+    else {
+      int gpus = 1;
+      if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) gpus = 1;
+      const unsigned hc = std::thread::hardware_concurrency();
+      T = (int)(hc ? hc : 8) / gpus;
+      if (T > 4) T = 4;          // measured (B200 box, 16 cores, 32 MB of scalars): 2 threads 8.0 ms, 4: 7.7, 8: 8.3 per call
+    }
+    if (T < 2) T = 2;
+    if (T > DeviceCtx::STAGE_SLOTS / 2) T = DeviceCtx::STAGE_SLOTS / 2;
     for (int w = 0; w < T; w++) std::thread([this, w] { worker(w); }).detach();
   }
   void worker(int w) {
@@ -263,7 +278,7 @@ struct StagePool {
         cv_work.wait(lk, [&] { return gen != seen; });
         seen = gen;
       }
-      constexpr int R = DeviceCtx::STAGE_SLOTS;
+      const int R = 2 * T;
       constexpr size_t CH = DeviceCtx::STAGE_BYTES;
       const size_t nchunks = (bytes + CH - 1) / CH;
       for (size_t i = w; i < nchunks; i += T) {
