@@ -566,11 +566,11 @@ def test_group_fft_next_row(zk, curve):
 
 def test_very_large_batch_is_split(zk):
     """nmsm * W exceeds the 65535 limit of a grid dimension: the batch is processed in sub-batches."""
-    curve, n, nmsm = "bn128", 8, 1500          # n = 8 -> c = 1..2 -> W >= 128: 1500 * W > 65535
+    curve, n, nmsm = "bn128", 8, 3000          # n = 8 -> c = 2..3 -> W >= 43 (GLV halves): 3000 * W > 65535
     pts = refs.chain_points(curve, n)
     sc = np.stack([refs.random_scalars(curve, n, seed=7000 + i) for i in range(nmsm)])
     got = zk.msm_batch(curve, sc, pts, mont=False, out="affine")
-    for i in (0, 1, 511, 512, 1499):
+    for i in (0, 1, 511, 512, 1499, 1500, 2999):
         assert got[i].tobytes() == cpu_affine(curve, sc[i], pts).tobytes(), i
     assert zk.last_stats()["nwindows"] * nmsm > 65535
 

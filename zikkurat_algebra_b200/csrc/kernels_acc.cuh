@@ -8,6 +8,7 @@
 
 #include "glv.cuh"
 #include "msm_common.cuh"
+#include "sort.cuh"
 
 namespace zk {
 
@@ -16,7 +17,7 @@ namespace zk {
 template <class C>
 __global__ void __launch_bounds__(256)
 k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int mont, int nbits, int c, int W,
-         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+         uint2* __restrict__ pairs) {
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n * (size_t)nmsm) return;
   size_t msm = gid / n, i = gid - msm * n;
@@ -37,9 +38,7 @@ k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int
   for (int w = 0; w < W; w++) {
     uint32_t key, neg;
     recode_digit(k.l, nbits, c, w, carry, key, neg);
-    size_t o = (seg0 + w) * n + i;
-    keys[o] = key;
-    vals[o] = (uint32_t)i | (neg << 31);
+    pairs[(seg0 + w) * n + i] = make_uint2(key, (uint32_t)i | (neg << 31));
   }
 }
 
@@ -49,7 +48,7 @@ k_recode(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int
 template <class C>
 __global__ void __launch_bounds__(256)
 k_recode_glv(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm, int mont, int c, int W,
-             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+             uint2* __restrict__ pairs) {
   using G = typename GlvOf<C>::type;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n * (size_t)nmsm) return;
@@ -80,9 +79,7 @@ k_recode_glv(const uint64_t* __restrict__ scalars, int nl64, size_t n, int nmsm,
     for (int w = 0; w < W; w++) {
       uint32_t key, dneg;
       recode_digit(h[half], G::BITS, c, w, carry, key, dneg);
-      size_t o = (seg0 + w) * n2 + idx;
-      keys[o] = key;
-      vals[o] = idx | ((key != 0 && (dneg != 0) != neg[half]) ? 0x80000000u : 0u);
+      pairs[(seg0 + w) * n2 + idx] = make_uint2(key, idx | ((key != 0 && (dneg != 0) != neg[half]) ? 0x80000000u : 0u));
     }
   }
 }
@@ -282,16 +279,15 @@ inline int accumulate_variant() {
 
 template <class C>
 void launch_recode(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int nbits, int c, int W,
-                   uint32_t* keys, uint32_t* vals) {
+                   uint2* pairs) {
   size_t tot = (size_t)nmsm * n;
-  k_recode<C><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(scalars, nl64, n, nmsm, mont, nbits, c, W, keys, vals);
+  k_recode<C><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(scalars, nl64, n, nmsm, mont, nbits, c, W, pairs);
 }
 template <class C>
-void launch_recode_glv(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int c, int W, uint32_t* keys,
-                       uint32_t* vals) {
+void launch_recode_glv(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int c, int W, uint2* pairs) {
   if constexpr (GlvOf<C>::available) {
     size_t tot = (size_t)nmsm * n;
-    k_recode_glv<C><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(scalars, nl64, n, nmsm, mont, c, W, keys, vals);
+    k_recode_glv<C><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(scalars, nl64, n, nmsm, mont, c, W, pairs);
   }
 }
 template <class C>
@@ -336,8 +332,8 @@ void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<t
 
 #define ZK_INSTANTIATE_ACC(C)                                                                                              \
   template int accumulate_resident_threads<C>();                                                                          \
-  template void launch_recode<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, int, uint32_t*, uint32_t*); \
-  template void launch_recode_glv<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, uint32_t*, uint32_t*);  \
+  template void launch_recode<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, int, uint2*);                  \
+  template void launch_recode_glv<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, uint2*);                \
   template void launch_glv_points<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*);                                    \
   template void launch_accumulate<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,     \
                                      uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);                      \

@@ -75,10 +75,11 @@ constexpr int FIXUP_FAN = 8;  // fan-in per level of the head fix-up tree (kerne
 enum OutMode : int { OUT_PROJ = 0, OUT_JAC = 1, OUT_AFFINE = 2, OUT_XYZZ = 3 };
 
 // ---- host-side launchers (defined next to their kernels, explicitly instantiated per curve) -------------
+// recoding: packed (key, value) pairs (sort.cuh)
 template <class C> void launch_recode(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont,
-                                      int nbits, int c, int W, uint32_t* keys, uint32_t* vals);
+                                      int nbits, int c, int W, uint2* pairs);
 template <class C> void launch_recode_glv(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int c, int W,
-                                          uint32_t* keys, uint32_t* vals);
+                                          uint2* pairs);
 template <class C> void launch_glv_points(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst);
 template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
                                           size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,

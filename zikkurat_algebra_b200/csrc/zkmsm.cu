@@ -543,10 +543,12 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
 
     // ---- work arrays (sized for the longest slice) ----
     const size_t pairs_max = (size_t)nseg * pmax;
-    uint32_t* keys[2] = {(uint32_t*)cx.ensure(B_KEYS0, pairs_max * 4), (uint32_t*)cx.ensure(B_KEYS1, pairs_max * 4)};
-    uint32_t* vals[2] = {(uint32_t*)cx.ensure(B_VALS0, pairs_max * 4), (uint32_t*)cx.ensure(B_VALS1, pairs_max * 4)};
+    // packed (key, value) pairs, ping-pong between the sorting passes; the last pass writes the separate sorted arrays
+    uint2* packed[2] = {(uint2*)cx.ensure(B_KEYS0, pairs_max * 8), (uint2*)cx.ensure(B_KEYS1, pairs_max * 8)};
+    uint32_t* keys_sorted = (uint32_t*)cx.ensure(B_VALS0, pairs_max * 4);
+    uint32_t* vals_sorted = (uint32_t*)cx.ensure(B_VALS1, pairs_max * 4);
     const int tiles_max = (int)((pmax + SORT_TILE - 1) / SORT_TILE);
-    uint32_t* cnt = (uint32_t*)cx.ensure(B_CNT, (size_t)nseg * SORT_RADIX * tiles_max * 4);
+    uint32_t* cnt = (uint32_t*)cx.ensure(B_CNT, sort_cnt_bytes(nseg, tiles_max));
     uint32_t* rowsum = (uint32_t*)cx.ensure(B_ROWSUM, (size_t)nseg * SORT_RADIX * 4);
     const size_t slice_stride = (size_t)nseg * NB;   // buckets per slice
     Mem* buckets = (Mem*)cx.ensure(B_BUCKETS, (size_t)K * slice_stride * sizeof(Mem));
@@ -730,22 +732,21 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       CK(cudaEventRecord(ge[3], s));
       g_launches++;
       const size_t pk = nk * F;          // pairs per segment of this slice
+      const int tiles = (int)((pk + SORT_TILE - 1) / SORT_TILE);
       if constexpr (GlvOf<C>::available) {
-        if (glv) launch_recode_glv<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, c, W, keys[0], vals[0]);
-        else launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, keys[0], vals[0]);
+        if (glv) launch_recode_glv<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, c, W, packed[0]);
+        else launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, packed[0]);
       } else {
-        launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, keys[0], vals[0]);
+        launch_recode<C>(s, d_scalars + (K == 1 ? 0 : lo[k]) * nl, nl, nk, nmsm, mont, nbits, c, W, packed[0]);
       }
       CK(cudaGetLastError());
       CK(cudaEventRecord(ge[5], s));
-      const int tiles = (int)((pk + SORT_TILE - 1) / SORT_TILE);
-      int cur = 0;
-      for (int shift = 0; shift < c; shift += 8) {
-        g_launches += 3;
-        sort_pass(s, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], pk, nseg, shift, cnt, rowsum, tiles);
-        CK(cudaGetLastError());
-        cur ^= 1;
-      }
+      // keys are 1 .. 2^(c-1) (0 = no insertion): c bits cover them
+      g_launches += sort_pairs(s, packed[0], packed[1], keys_sorted, vals_sorted, pk, nseg, c, cnt, rowsum, tiles);
+      CK(cudaGetLastError());
+      uint32_t* const keys[1] = {keys_sorted};
+      uint32_t* const vals[1] = {vals_sorted};
+      const int cur = 0;
       CK(cudaEventRecord(ge[4], s));
       // ---- bucket accumulation of this slice ----
       if (ploc == ZKB200_HOST) {
