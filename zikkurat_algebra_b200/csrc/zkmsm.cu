@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -454,6 +455,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   if (glv) nbits = 127;
   int c = 0, W = 0, K = 1;
   int trace_groups = 0, trace_g0[9] = {0};
+  const auto host_t0 = std::chrono::steady_clock::now();
+  double host_ms[4] = {0, 0, 0, 0};   // $ZKB200_TRACE: host time until the work arrays exist / all launches queued / the stream is done
+  auto host_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
   CK(cudaEventRecord(cx.ev[0], s));
   if (n == 0) {
     g_launches++;
@@ -481,10 +485,13 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       // insertion, buckets and chunk heads about two XYZZ records per bucket.  A batch that would not fit in what is
       // free (plus the workspaces this device already holds) is processed in halves instead of aborting in cudaMalloc.
       size_t fr = 0, tot = 0, held = 0;
-      CK(cudaMemGetInfo(&fr, &tot));
-      for (int i = 0; i < B_COUNT; i++) held += cx.cap[i];
-      const double need = (double)nmsm * W * ((double)(n * F) * 16.0 + (double)NB * 2.5 * sizeof(Mem)) + (double)nmsm * n * nl * 8.0;
-      if (need > 0.8 * (double)(fr + held)) {
+      const double need = (double)nmsm * W * ((double)(n * F) * 24.0 + (double)NB * 2.5 * sizeof(Mem)) + (double)nmsm * n * nl * 8.0;
+      // (the driver query costs 0.2 .. 3 ms: only asked when the batch is big enough to matter)
+      if (need > 8e9) {
+        CK(cudaMemGetInfo(&fr, &tot));
+        for (int i = 0; i < B_COUNT; i++) held += cx.cap[i];
+      }
+      if (need > 8e9 && need > 0.8 * (double)(fr + held)) {
         const int half = nmsm / 2;
         const int out_c = out_mode == OUT_AFFINE ? 2 : (out_mode == OUT_XYZZ ? 4 : 3);
         run_msm<C>(cx, half, n, scalars, sloc, points, ploc, nl, mont, out_mode, c, out, out_loc);
@@ -717,6 +724,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     cx.pl.big[1] = cx.pl.s_big[1];
     cx.pl.chain[1] = cx.pl.s_chain[1];
 
+    host_ms[0] = host_now();
     for (int k = 0; k < K; k++) {
       const size_t nk = lo[k + 1] - lo[k];
       if (nk == 0) continue;
@@ -923,8 +931,10 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     CK(cudaMemcpyAsync(h_out, d_out, (size_t)nmsm * 4 * L * 4, cudaMemcpyDeviceToHost, s));
   }
   CK(cudaEventRecord(cx.ev[8], s));
+  host_ms[1] = host_now();
   CK(cudaStreamSynchronize(s));
   CK(cudaStreamSynchronize(cx.s_copy));
+  host_ms[2] = host_now();
   if (out_loc != ZKB200_DEVICE)
     for (int m = 0; m < nmsm; m++)
       memcpy((uint32_t*)out + (size_t)m * out_coords * L, h_out + (size_t)m * 4 * L, (size_t)out_coords * L * 4);
@@ -952,8 +962,8 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     CK(cudaEventElapsedTime(&t_sorted, cx.ev[0], cx.gev[4]));
     CK(cudaEventElapsedTime(&t_lanes, cx.ev[0], cx.ev[5]));
     CK(cudaEventElapsedTime(&t_post, cx.ev[0], cx.ev[6]));
-    fprintf(stderr, "[zkmsm_b200 trace] n=%zu c=%d W=%d R=%d sorted %.3f lanes_done %.3f post_done %.3f total %.3f |", n, c, W,
-            st.aff_levels, t_sorted, t_lanes, t_post, st.ms[8]);
+    fprintf(stderr, "[zkmsm_b200 trace] n=%zu c=%d W=%d R=%d sorted %.3f lanes_done %.3f post_done %.3f total %.3f | host: arrays %.3f "
+            "queued %.3f done %.3f |", n, c, W, st.aff_levels, t_sorted, t_lanes, t_post, st.ms[8], host_ms[0], host_ms[1], host_ms[2]);
     if (trace_groups > 1)
       for (int g = trace_groups - 1; g >= 0; g--) {
         float a = 0, b = 0;
