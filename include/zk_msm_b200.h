@@ -201,6 +201,10 @@ void zkb200_selftest_field(int field, int op, long n, const uint64_t *a, const u
 void zkb200_selftest_group(int curve, int op, long n, const uint64_t *p1, const uint64_t *z1, const uint64_t *p2,
                            const uint64_t *z2, uint64_t *out_affine);
 
+/* Device time (ms, CUDA events on the launching stream) of the kernels of the most recent batch conversion, NTT or
+ * group-FFT call on the current device, copies excluded (the roofline numerator's time for bench.py --row). */
+float zkb200_last_op_ms(void);
+
 /* Number of kernels this library has launched since it was loaded (bench.py's "gpu_launches"). */
 long long zkb200_launch_count(void);
 

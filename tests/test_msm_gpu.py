@@ -318,6 +318,21 @@ def test_batch_conversions_next_row(zk, curve):
     # a larger round trip through MSM-independent data: 2^16 chain points -> proj -> affine
     big = refs.chain_points(curve, 1 << 16)
     assert zk.batch_to_affine(curve, zk.batch_from_affine(curve, big, "jac"), "jac").tobytes() == big.tobytes()
+    # large arrays take the one-inversion-per-call path (batch inversion tree): random denominators, some Z = 0, against
+    # the reference's own per-point <curve>_G1_{proj,jac}_to_affine applied to every record
+    from tests.test_device_primitives import cpu_map2
+    n2 = 9001
+    base = refs.chain_points(curve, n2, s0=0x4242, s1=0x99)
+    for rep in ("proj", "jac"):
+        recs = np.zeros((n2, 3 * L), np.uint64)
+        for i in range(n2):
+            x, y = cv.affine_from_bytes(base[i].tobytes())
+            z = 0 if i % 1000 == 7 else rng.randrange(1, cv.p)
+            X = x * (z if rep == "proj" else z * z) % cv.p if z else rng.randrange(1, cv.p)
+            Y = y * (z if rep == "proj" else z * z * z) % cv.p if z else rng.randrange(1, cv.p)
+            recs[i] = np.frombuffer(cv.fp_to_bytes(X) + cv.fp_to_bytes(Y) + cv.fp_to_bytes(z), dtype=np.uint64)
+        want = cpu_map2(f"{curve}_G1_{rep}_to_affine", recs, 2 * L)
+        assert zk.batch_to_affine(curve, recs, rep).tobytes() == want.tobytes(), rep
 
 
 def test_concurrent_callers_are_serialised_correctly(zk):

@@ -95,8 +95,8 @@ k_glv_points(const uint32_t* __restrict__ src, size_t n, uint32_t* __restrict__ 
   if (i >= n) return;
   constexpr int PW = (2 * P::L) / 4;
   const uint4* q = reinterpret_cast<const uint4*>(src + i * (2 * P::L));
-  uint4* d0 = reinterpret_cast<uint4*>(dst + i * (2 * P::L));
-  uint4* d1 = reinterpret_cast<uint4*>(dst + (n + i) * (2 * P::L));
+  uint4* d0 = reinterpret_cast<uint4*>(dst + i * own_stride<P>());
+  uint4* d1 = reinterpret_cast<uint4*>(dst + (n + i) * own_stride<P>());
   uint32_t t[2 * P::L];
 #pragma unroll
   for (int kq = 0; kq < PW; kq++) {
@@ -126,7 +126,7 @@ k_glv_points(const uint32_t* __restrict__ src, size_t n, uint32_t* __restrict__ 
 template <class C, bool CALLS, int MINB = (C::Fp::L <= 8 ? 4 : (C::Fp::L <= 12 ? 3 : 2))>
 __global__ void __launch_bounds__(128, MINB)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-             const uint32_t* __restrict__ points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
+             const uint32_t* __restrict__ points, int pstride, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
              uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets,
              XyzzMem<typename C::Fp>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
   using P = typename C::Fp;
@@ -146,7 +146,7 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   constexpr int PW = (2 * P::L) / 4;                 // 16-byte words per affine point
   __shared__ uint4 stage[2][PW][128];
   auto prefetch = [&](int buf, uint32_t v) {
-    const uint4* src = reinterpret_cast<const uint4*>(points + (size_t)(v & 0x7fffffffu) * (2 * P::L));
+    const uint4* src = reinterpret_cast<const uint4*>(points + (size_t)(v & 0x7fffffffu) * pstride);
 #pragma unroll
     for (int w = 0; w < PW; w++) {
       unsigned dst = (unsigned)__cvta_generic_to_shared(&stage[buf][w][threadIdx.x]);
@@ -295,18 +295,18 @@ void launch_glv_points(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* 
   if constexpr (GlvOf<C>::available) k_glv_points<C><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(src, n, dst);
 }
 template <class C>
-void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int nseg,
+void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, int pstride, size_t n, int nseg,
                        int chunk, uint32_t chunks_per_seg, uint32_t NB, XyzzMem<typename C::Fp>* buckets,
                        XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
   size_t nthreads = (size_t)nseg * chunks_per_seg;
   if (accumulate_variant<C>() == 2)
-    k_accumulate<C, true, 4><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg,
+    k_accumulate<C, true, 4><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, pstride, n, nseg, chunk, chunks_per_seg,
                                                                                NB, buckets, heads, head_keys);
   else if (accumulate_variant<C>() == 1)
-    k_accumulate<C, true><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg,
+    k_accumulate<C, true><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, pstride, n, nseg, chunk, chunks_per_seg,
                                                                             NB, buckets, heads, head_keys);
   else
-    k_accumulate<C, false><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, n, nseg, chunk, chunks_per_seg,
+    k_accumulate<C, false><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(keys, vals, points, pstride, n, nseg, chunk, chunks_per_seg,
                                                                              NB, buckets, heads, head_keys);
 }
 template <class C>
@@ -335,7 +335,7 @@ void launch_fixup_level(cudaStream_t s, const uint32_t* keys_in, const XyzzMem<t
   template void launch_recode<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, int, uint2*);                  \
   template void launch_recode_glv<C>(cudaStream_t, const uint64_t*, int, size_t, int, int, int, int, uint2*);                \
   template void launch_glv_points<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*);                                    \
-  template void launch_accumulate<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int, int,     \
+  template void launch_accumulate<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, int, size_t, int, int, \
                                      uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);                      \
   template void launch_fixup_level<C>(cudaStream_t, const uint32_t*, const XyzzMem<C::Fp>*, uint32_t, uint32_t*,           \
                                       XyzzMem<C::Fp>*, uint32_t, int, uint32_t, XyzzMem<C::Fp>*, int);

@@ -50,13 +50,13 @@ ZK_D void st_fe(uint32_t* p, const Fe<P>& v) {
 }
 
 template <class P>
-ZK_D const uint32_t* aff_addr(const uint32_t* points, const uint32_t* tmp, uint32_t ref) {
-  return ((ref & AFF_TEMP) ? tmp : points) + (size_t)(ref & AFF_IDX) * (2 * P::L);
+ZK_D const uint32_t* aff_addr(const uint32_t* points, int pstride, const uint32_t* tmp, uint32_t ref) {
+  return (ref & AFF_TEMP) ? tmp + (size_t)(ref & AFF_IDX) * own_stride<P>() : points + (size_t)(ref & AFF_IDX) * pstride;
 }
 // the point a ref names, sign applied; inf = it is the point at infinity
 template <class P>
-ZK_D Affine<P> aff_load(const uint32_t* points, const uint32_t* tmp, uint32_t ref, bool& inf) {
-  const uint32_t* a = aff_addr<P>(points, tmp, ref);
+ZK_D Affine<P> aff_load(const uint32_t* points, int pstride, const uint32_t* tmp, uint32_t ref, bool& inf) {
+  const uint32_t* a = aff_addr<P>(points, pstride, tmp, ref);
   Affine<P> p;
   p.x = ld_fe<P>(a);
   p.y = ld_fe<P>(a + P::L);
@@ -66,7 +66,7 @@ ZK_D Affine<P> aff_load(const uint32_t* points, const uint32_t* tmp, uint32_t re
 }
 template <class P>
 ZK_D void aff_store(uint32_t* tmp, size_t slot, const Affine<P>& p, bool inf) {
-  uint32_t* a = tmp + slot * (2 * P::L);
+  uint32_t* a = tmp + slot * own_stride<P>();
   if (inf) {
     uint4* q = reinterpret_cast<uint4*>(a);
 #pragma unroll
@@ -111,7 +111,7 @@ ZK_D AffPair aff_read_pair(const uint32_t* __restrict__ keys, const uint32_t* __
 template <class C, bool LEVEL0>
 __global__ void __launch_bounds__(AFF_THREADS)
 k_aff_prod(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
-           uint32_t nm, uint32_t total, const uint32_t* points, const uint32_t* tmp, uint32_t* __restrict__ pre,
+           uint32_t nm, uint32_t total, const uint32_t* points, int pstride, const uint32_t* tmp, uint32_t* __restrict__ pre,
            uint32_t* __restrict__ tot, int B) {
   using P = typename C::Fp;
   constexpr bool CALLS = (P::L > 8);
@@ -125,13 +125,13 @@ k_aff_prod(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
     AffPair a = aff_read_pair<LEVEL0>(keys, vals, st_in, nin, seg, i);
     if (!(a.Ltk == a.Rhk && a.Ltk != 0)) continue;
     // x coordinates decide almost always; the full points are fetched only for the exceptional shapes
-    const uint32_t* a1 = aff_addr<P>(points, tmp, a.Ltr);
-    const uint32_t* a2 = aff_addr<P>(points, tmp, a.Rhr);
+    const uint32_t* a1 = aff_addr<P>(points, pstride, tmp, a.Ltr);
+    const uint32_t* a2 = aff_addr<P>(points, pstride, tmp, a.Rhr);
     Fe<P> x1 = ld_fe<P>(a1), x2 = ld_fe<P>(a2), d;
     int cls;
     if (x1.l[P::L - 1] == 0xffffffffu || x2.l[P::L - 1] == 0xffffffffu || fe_eq<P>(x1, x2)) {
       bool i1, i2;
-      Affine<P> p1 = aff_load<P>(points, tmp, a.Ltr, i1), p2 = aff_load<P>(points, tmp, a.Rhr, i2);
+      Affine<P> p1 = aff_load<P>(points, pstride, tmp, a.Ltr, i1), p2 = aff_load<P>(points, pstride, tmp, a.Rhr, i2);
       cls = aff_classify<P>(p1, i1, p2, i2, d);
     } else {
       d = fe_sub<P>(x2, x1);
@@ -160,7 +160,7 @@ constexpr size_t aff_stage_bytes() { return (size_t)2 * aff_stage_words<P>() * A
 template <class C, bool LEVEL0, bool LAST, bool CALLS>
 __global__ void __launch_bounds__(AFF_THREADS)
 k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
-          uint32_t nm, uint32_t total, const uint32_t* points, uint32_t* tmp, uint32_t tmp_off, const uint32_t* __restrict__ pre,
+          uint32_t nm, uint32_t total, const uint32_t* points, int pstride, uint32_t* tmp, uint32_t tmp_off, const uint32_t* __restrict__ pre,
           const uint32_t* __restrict__ totinv, uint4* __restrict__ st_out, uint32_t* __restrict__ keys_out,
           uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets, int B) {
   using P = typename C::Fp;
@@ -177,8 +177,8 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
     i = m - seg * nm;
     a = aff_read_pair<LEVEL0>(keys, vals, st_in, nin, seg, i);
     if (a.Ltk == a.Rhk && a.Ltk != 0) {
-      const uint4* s1 = reinterpret_cast<const uint4*>(aff_addr<P>(points, tmp, a.Ltr));
-      const uint4* s2 = reinterpret_cast<const uint4*>(aff_addr<P>(points, tmp, a.Rhr));
+      const uint4* s1 = reinterpret_cast<const uint4*>(aff_addr<P>(points, pstride, tmp, a.Ltr));
+      const uint4* s2 = reinterpret_cast<const uint4*>(aff_addr<P>(points, pstride, tmp, a.Rhr));
       const uint4* s3 = reinterpret_cast<const uint4*>(pre + (size_t)m * P::L);
       uint4* dst = aff_stage + (size_t)buf * NW * AFF_THREADS + threadIdx.x;
 #pragma unroll
@@ -251,7 +251,7 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
         for (int k = 0; k < 2; k++) {
           if (pl.st_key[k] != 0) {
             bool inf;
-            Affine<P> p = aff_load<P>(points, tmp, pl.st_ref[k], inf);
+            Affine<P> p = aff_load<P>(points, pstride, tmp, pl.st_ref[k], inf);
             aff_to_bucket<P>(bseg + (pl.st_key[k] - 1), p, inf);
           }
         }
@@ -468,7 +468,7 @@ int batch_invert(cudaStream_t s, const uint32_t* E0, size_t T0, uint32_t* ws, ui
 // previous chunk's last run), every other run is complete for this level and is stored to its bucket.
 template <class C, bool CALLS, int MINB = (C::Fp::L <= 8 ? 4 : (C::Fp::L <= 12 ? 3 : 2))>
 __global__ void __launch_bounds__(128, MINB)
-k_accumulate_rec(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ points,
+k_accumulate_rec(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ points, int pstride,
                  const uint32_t* __restrict__ tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
                  XyzzMem<typename C::Fp>* __restrict__ buckets, XyzzMem<typename C::Fp>* __restrict__ heads,
                  uint32_t* __restrict__ head_keys) {
@@ -485,7 +485,7 @@ k_accumulate_rec(const uint32_t* __restrict__ keys, const uint32_t* __restrict__
   constexpr int PW = (2 * P::L) / 4;
   __shared__ uint4 stage[2][PW][128];
   auto prefetch = [&](int buf, uint32_t v) {
-    const uint4* src = reinterpret_cast<const uint4*>(aff_addr<P>(points, tmp_points, v));
+    const uint4* src = reinterpret_cast<const uint4*>(aff_addr<P>(points, pstride, tmp_points, v));
 #pragma unroll
     for (int w = 0; w < PW; w++) {
       unsigned dst = (unsigned)__cvta_generic_to_shared(&stage[buf][w][threadIdx.x]);
@@ -556,12 +556,12 @@ k_accumulate_rec(const uint32_t* __restrict__ keys, const uint32_t* __restrict__
 }
 
 template <class C>
-void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
+void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, int pstride,
                            const uint32_t* tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
                            XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
   size_t nthreads = (size_t)nseg * chunks_per_seg;
   k_accumulate_rec<C, (C::Fp::L > 8)><<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(
-      keys, vals, points, tmp_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
+      keys, vals, points, pstride, tmp_points, n, nseg, chunk, chunks_per_seg, NB, buckets, heads, head_keys);
 }
 
 // ---- host helpers -------------------------------------------------------------------------------------------------
@@ -595,7 +595,7 @@ inline void aff_allow_smem(K kernel, size_t smem) {
 
 // ---- host driver: R levels over sorted pairs, then the records ------------------------------------------------------
 template <class C>
-int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, size_t n, int R,
+int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, int pstride, size_t n, int R,
                        uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w, int chunk_rec, uint32_t cps,
                        XyzzMem<typename C::Fp>* heads, uint32_t* head_keys) {
   using P = typename C::Fp;
@@ -645,8 +645,8 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
     uint32_t* tot = w.binv + binv_base[g] * P::L;
     const size_t T0 = (size_t)blocks * AFF_THREADS;
-    if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot, B);
-    else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, pre, tot, B);
+    if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, pre, tot, B);
+    else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, pre, tot, B);
     launches++;
     if (big[g] != chain[g]) { ZK_AFF_CK(cudaEventRecord(ln.ev_a[g], big[g])); ZK_AFF_CK(cudaStreamWaitEvent(chain[g], ln.ev_a[g], 0)); }
     launches += batch_invert<P>(chain[g], tot, T0, tot + T0 * P::L, &inv[g]);
@@ -671,11 +671,11 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
   do {                                                                                                                        \
     if (inl) {                                                                                                                \
       aff_allow_smem(k_aff_add<C, L0, LA, false>, smem);                                                                      \
-      k_aff_add<C, L0, LA, false><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off, \
+      k_aff_add<C, L0, LA, false><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, tmp_off, \
                                                                          pre, inv[g], st_out, ko, vo, NB, bg, B);             \
     } else {                                                                                                                  \
       aff_allow_smem(k_aff_add<C, L0, LA, true>, smem);                                                                       \
-      k_aff_add<C, L0, LA, true><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, w.tmp, tmp_off,  \
+      k_aff_add<C, L0, LA, true><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, tmp_off,  \
                                                                         pre, inv[g], st_out, ko, vo, NB, bg, B);              \
     }                                                                                                                         \
   } while (0)
@@ -689,7 +689,7 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
   };
   const uint32_t nrec = 2 * nm_l[R - 1];   // surviving record slots per segment
   auto do_records = [&](int g) {
-    launch_accumulate_rec<C>(big[g], w.keys_out + (size_t)seg0[g] * nrec, w.vals_out + (size_t)seg0[g] * nrec, points, w.tmp, nrec,
+    launch_accumulate_rec<C>(big[g], w.keys_out + (size_t)seg0[g] * nrec, w.vals_out + (size_t)seg0[g] * nrec, points, pstride, w.tmp, nrec,
                              segs[g], chunk_rec, cps, NB, buckets + (size_t)seg0[g] * NB, heads + (size_t)seg0[g] * cps,
                              head_keys + (size_t)seg0[g] * cps);
     launches++;
@@ -708,11 +708,17 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
   return launches;
 }
 
+template <class C>
+int launch_batch_invert(cudaStream_t s, const uint32_t* E0, size_t T0, uint32_t* ws, uint32_t** inv_out) {
+  return batch_invert<typename C::Fp>(s, E0, T0, ws, inv_out);
+}
+
 #define ZK_INSTANTIATE_AFF(C)                                                                                             \
-  template int launch_affine_tree<C>(const AffLanes&, const uint32_t*, const uint32_t*, const uint32_t*, size_t, int,     \
+  template int launch_batch_invert<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, uint32_t**);                      \
+  template int launch_affine_tree<C>(const AffLanes&, const uint32_t*, const uint32_t*, const uint32_t*, int, size_t, int, \
                                      uint32_t, XyzzMem<C::Fp>*, const AffWork&, int, uint32_t, XyzzMem<C::Fp>*,           \
                                      uint32_t*);                                                                          \
-  template void launch_accumulate_rec<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, \
+  template void launch_accumulate_rec<C>(cudaStream_t, const uint32_t*, const uint32_t*, const uint32_t*, int, const uint32_t*, \
                                          size_t, int, int, uint32_t, uint32_t, XyzzMem<C::Fp>*, XyzzMem<C::Fp>*, uint32_t*);
 
 #endif  // __CUDACC__

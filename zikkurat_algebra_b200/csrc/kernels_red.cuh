@@ -299,6 +299,44 @@ k_batch_to_affine(const uint32_t* __restrict__ src, size_t n, uint32_t* __restri
     }
   }
 }
+// The same conversion for LARGE arrays with ONE field inversion per call: the Z coordinates (1 where Z = 0) go through the
+// batch inversion tree of the affine pre-reduction (kernels_aff.cuh: batch_invert, 3 multiplications per element), then
+// every point is scaled by its own 1/Z.  2 + 3 (proj) or 4 + 3 (jac) multiplications per point instead of a quarter of a
+// full inversion.  Same canonical output.
+template <class C>
+__global__ void __launch_bounds__(256)
+k_convert_z(const uint32_t* __restrict__ src, size_t n, uint32_t* __restrict__ z_out) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<P> z = read_fe<P>(src + i * 3 * L + 2 * L);
+  if (fe_is_zero<P>(z)) z = fe_one<P>();
+  write_fe<P>(z_out + i * L, z);
+}
+template <class C, bool JAC>
+__global__ void __launch_bounds__(128)
+k_convert_apply(const uint32_t* __restrict__ src, const uint32_t* __restrict__ zinv, size_t n, uint32_t* __restrict__ dst) {
+  using P = typename C::Fp;
+  constexpr int L = P::L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* s = src + i * 3 * L;
+  uint32_t* o = dst + i * 2 * L;
+  if (fe_is_zero<P>(read_fe<P>(s + 2 * L))) {
+    for (int k = 0; k < 2 * L; k++) o[k] = 0xffffffffu;
+    return;
+  }
+  Fe<P> zi = read_fe<P>(zinv + i * L), X = read_fe<P>(s), Y = read_fe<P>(s + L);
+  if (JAC) {
+    Fe<P> zi2 = fe_mul_call<P>(zi, zi);
+    write_fe<P>(o, fe_mul_call<P>(X, zi2));
+    write_fe<P>(o + L, fe_mul_call<P>(Y, fe_mul_call<P>(zi2, zi)));
+  } else {
+    write_fe<P>(o, fe_mul_call<P>(X, zi));
+    write_fe<P>(o + L, fe_mul_call<P>(Y, zi));
+  }
+}
 // <curve>_G1_{proj,jac}_batch_from_affine (bn128_G1_proj.c:147-155 -> :120-128; bn128_G1_jac.c:138-145 -> :105-116)
 template <class C, bool JAC>
 __global__ void __launch_bounds__(256)
@@ -324,6 +362,15 @@ void launch_batch_to_affine(cudaStream_t s, const uint32_t* src, size_t n, uint3
   size_t threads = (n + TOAFF_BATCH - 1) / TOAFF_BATCH;
   if (jac) k_batch_to_affine<C, true><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(src, n, dst);
   else k_batch_to_affine<C, false><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(src, n, dst);
+}
+template <class C>
+void launch_convert_z(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* z_out) {
+  k_convert_z<C><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, n, z_out);
+}
+template <class C>
+void launch_convert_apply(cudaStream_t s, const uint32_t* src, const uint32_t* zinv, size_t n, uint32_t* dst, int jac) {
+  if (jac) k_convert_apply<C, true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(src, zinv, n, dst);
+  else k_convert_apply<C, false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(src, zinv, n, dst);
 }
 template <class C>
 void launch_batch_from_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac) {
@@ -374,6 +421,8 @@ void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, i
   template void launch_tail_group<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, XyzzMem<C::Fp>*);                 \
   template void launch_gen_chain<C>(cudaStream_t, const uint32_t*, unsigned long long, size_t, uint32_t*);               \
   template void launch_batch_to_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);                         \
+  template void launch_convert_z<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*);                                     \
+  template void launch_convert_apply<C>(cudaStream_t, const uint32_t*, const uint32_t*, size_t, uint32_t*, int);           \
   template void launch_batch_from_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);
 
 }  // namespace zk

@@ -70,6 +70,13 @@ ZK_D Affine<P> load_affine(const uint32_t* __restrict__ pts, uint32_t i) {
 }
 
 
+// Words between consecutive affine records of the library's OWN point arrays (the GLV-expanded points, the affine
+// tree's temporaries); the caller's array has 2L-word records, kernels take the stride of `points` as an argument.
+// Padding 12-limb records from 96 to 128 bytes (a record then never straddles a 128-byte line, the x coordinate alone is
+// one aligned 64-byte DRAM burst) was measured and LOST: BLS12-381 2^20 6.38 -> 6.69 ms -- the arrays grow by a third and
+// fall further out of the 126 MB L2, which costs more than the straddling did (profiles/r2_notes.md).
+template <class P> __host__ __device__ constexpr int own_stride() { return 2 * P::L; }
+
 constexpr int FIXUP_FAN = 8;  // fan-in per level of the head fix-up tree (kernels_acc.cuh)
 
 enum OutMode : int { OUT_PROJ = 0, OUT_JAC = 1, OUT_AFFINE = 2, OUT_XYZZ = 3 };
@@ -81,7 +88,7 @@ template <class C> void launch_recode(cudaStream_t s, const uint64_t* scalars, i
 template <class C> void launch_recode_glv(cudaStream_t s, const uint64_t* scalars, int nl64, size_t n, int nmsm, int mont, int c, int W,
                                           uint2* pairs);
 template <class C> void launch_glv_points(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst);
-template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
+template <class C> void launch_accumulate(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, int pstride,
                                           size_t n, int nseg, int chunk, uint32_t chunks_per_seg, uint32_t NB,
                                           XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys);
 template <class C> int accumulate_resident_threads();
@@ -157,10 +164,10 @@ struct AffLanes {
 // R levels of pairwise affine sums over the sorted pairs of the lanes' segments, then the XYZZ accumulation of the
 // surviving records (chunk_rec record slots per thread, cps threads per segment; heads / head_keys indexed by segment
 // as for launch_accumulate).  keys / vals / buckets / heads are the arrays of ALL segments.
-template <class C> int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
+template <class C> int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, int pstride,
                                           size_t n, int R, uint32_t NB, XyzzMem<typename C::Fp>* buckets, const AffWork& w,
                                           int chunk_rec, uint32_t cps, XyzzMem<typename C::Fp>* heads, uint32_t* head_keys);
-template <class C> void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points,
+template <class C> void launch_accumulate_rec(cudaStream_t s, const uint32_t* keys, const uint32_t* vals, const uint32_t* points, int pstride,
                                               const uint32_t* tmp_points, size_t n, int nseg, int chunk, uint32_t chunks_per_seg,
                                               uint32_t NB, XyzzMem<typename C::Fp>* buckets, XyzzMem<typename C::Fp>* heads,
                                               uint32_t* head_keys);
@@ -178,6 +185,10 @@ template <class C> void launch_tail_group(cudaStream_t s, const XyzzMem<typename
                                           XyzzMem<typename C::Fp>* out);
 template <class C> void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out);
 template <class C> void launch_batch_to_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);
+template <class C> void launch_convert_z(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* z_out);
+template <class C> void launch_convert_apply(cudaStream_t s, const uint32_t* src, const uint32_t* zinv, size_t n, uint32_t* dst, int jac);
+// batch inversion of T0 non-zero field elements (kernels_aff.cuh): workspace of binv_workspace_elems(T0) elements, result in *inv_out
+template <class C> int launch_batch_invert(cudaStream_t s, const uint32_t* E0, size_t T0, uint32_t* ws, uint32_t** inv_out);
 template <class C> void launch_batch_from_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);
 template <class C> void launch_gen_chain(cudaStream_t s, const uint32_t* p0d, unsigned long long start, size_t n, uint32_t* out);
 

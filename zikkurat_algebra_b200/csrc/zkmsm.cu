@@ -86,6 +86,7 @@ struct DeviceCtx {
   std::mutex mu;              // one MSM at a time per device (workspaces are shared)
   Stats stats;
   int resident[4] = {0, 0, 0, 0};   // resident k_accumulate threads of this device, per curve id (filled under mu)
+  float last_op_ms = 0.f;           // device time of the kernels of the last conversion / NTT / group FFT call (no copies)
   struct StagePool* pool = nullptr; // persistent staging threads for pageable sources (created on first use)
   // Device-resident copies of point arrays the caller keeps passing (the SRS of a KZG prover), see srs_lookup
   struct SrsEntry { const void* host; size_t bytes; uint64_t fp; int curve; void* dev; uint64_t last_use; };
@@ -546,7 +547,9 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     if (sloc == ZKB200_HOST) d_scalars = (const uint64_t*)cx.ensure(B_SCALARS, (size_t)nmsm * n * nl * 8);
     if (ploc == ZKB200_HOST) d_points = (const uint32_t*)cx.ensure(B_POINTS, n * (size_t)(2 * L) * 4);
     // GLV: slice k's points are expanded to [P ; phi(P)] (2 nk records) at record offset 2 lo[k] of this array
-    uint32_t* glv_points = glv ? (uint32_t*)cx.ensure(B_GLV_POINTS, 2 * n * (size_t)(2 * L) * 4) : nullptr;
+    constexpr int OS = own_stride<P>();           // record stride (words) of the library's own point arrays
+    const int pstride = glv ? OS : 2 * L;         // stride of the array the pairs' indices refer to
+    uint32_t* glv_points = glv ? (uint32_t*)cx.ensure(B_GLV_POINTS, 2 * n * (size_t)OS * 4) : nullptr;
 
     // ---- work arrays (sized for the longest slice) ----
     const size_t pairs_max = (size_t)nseg * pmax;
@@ -587,7 +590,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (pairs_max >= ((size_t)1 << 30) || n * F >= ((size_t)1 << 30)) R = 0;   // 30-bit refs
       if (R > 0) {   // workspace guard: temporary points + running products
         AffSizes z = aff_sizes(pmax, nseg, R);
-        if ((z.tmp_points * 2 + z.pre_elems) * (size_t)L * 4 > ((size_t)48 << 30)) R = 0;
+        if ((z.tmp_points * OS + z.pre_elems * L) * (size_t)4 > ((size_t)48 << 30)) R = 0;
       }
     }
     st.aff_levels = R;
@@ -684,7 +687,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     if (R > 0) {
       az = aff_sizes(pmax, nseg, R);
       binv_stride = az.binv_elems + 64;
-      aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)(2 * L) * 4);
+      aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)OS * 4);
       aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, az.pre_elems * (size_t)L * 4);
       aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, 4 * binv_stride * (size_t)L * 4);
       aw.st[0] = (uint4*)cx.ensure(B_AFF_ST0, az.st0 * 16 + 16);
@@ -764,7 +767,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       const uint32_t* pts_k = d_points + lo[k] * (size_t)(2 * L);
       if constexpr (GlvOf<C>::available) {
         if (glv) {   // on the copy stream: behind this slice's upload, under the recoding and the sort of the pairs
-          uint32_t* ext = glv_points + 2 * lo[k] * (size_t)(2 * L);
+          uint32_t* ext = glv_points + 2 * lo[k] * (size_t)OS;
           g_launches++;
           launch_glv_points<C>(cx.s_copy, pts_k, nk, ext);
           CK(cudaGetLastError());
@@ -813,14 +816,14 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
         }
         if constexpr (HasAffineTree<C>::value) {
           if (R > 0)
-            g_launches += launch_affine_tree<C>(ln, keys[cur], vals[cur], pts_k, pk, R, NB, kb_, aw, chunk_rec, cps, heads, head_keys);
+            g_launches += launch_affine_tree<C>(ln, keys[cur], vals[cur], pts_k, pstride, pk, R, NB, kb_, aw, chunk_rec, cps, heads, head_keys);
         }
         for (int l = 0; l < ln.n; l++) {
           const int s0 = ln.seg0[l], ns = ln.segs[l];
           cudaStream_t sl = ln.big[l];
           if (R == 0) {
             g_launches++;
-            launch_accumulate<C>(sl, keys[cur] + (size_t)s0 * pk, vals[cur] + (size_t)s0 * pk, pts_k, pk, ns, chunk, cps, NB,
+            launch_accumulate<C>(sl, keys[cur] + (size_t)s0 * pk, vals[cur] + (size_t)s0 * pk, pts_k, pstride, pk, ns, chunk, cps, NB,
                                  kb_ + (size_t)s0 * NB, heads + (size_t)s0 * cps, head_keys + (size_t)s0 * cps);
           }
           CK(cudaGetLastError());
@@ -1228,12 +1231,27 @@ void run_convert(int N, const uint64_t* src, uint64_t* tgt, int jac, int to_affi
   uint32_t* d_out = (uint32_t*)cx.ensure(B_KEYS0, out_bytes);
   cudaStream_t s = cx.s_main;
   CK(cudaMemcpyAsync(d_in, src, in_bytes, cudaMemcpyHostToDevice, s));
-  g_launches++;
-  if (to_affine) launch_batch_to_affine<C>(s, d_in, n, d_out, jac);
-  else launch_batch_from_affine<C>(s, d_in, n, d_out, jac);
+  CK(cudaEventRecord(cx.ev[0], s));
+  if (to_affine && n >= 4096) {
+    // one inversion for the whole array: Z coordinates -> batch inversion tree -> scale every point by its own 1/Z
+    uint32_t* d_z = (uint32_t*)cx.ensure(B_AFF_PRE, n * (size_t)L * 4);
+    uint32_t* d_ws = (uint32_t*)cx.ensure(B_AFF_BINV, (binv_workspace_elems(n) + 64) * (size_t)L * 4);
+    uint32_t* d_inv = nullptr;
+    launch_convert_z<C>(s, d_in, n, d_z);
+    CK(cudaGetLastError());
+    g_launches += 2 + launch_batch_invert<C>(s, d_z, n, d_ws, &d_inv);
+    CK(cudaGetLastError());
+    launch_convert_apply<C>(s, d_in, d_inv, n, d_out, jac);
+  } else {
+    g_launches++;
+    if (to_affine) launch_batch_to_affine<C>(s, d_in, n, d_out, jac);
+    else launch_batch_from_affine<C>(s, d_in, n, d_out, jac);
+  }
   CK(cudaGetLastError());
+  CK(cudaEventRecord(cx.ev[1], s));
   CK(cudaMemcpyAsync(tgt, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(&cx.last_op_ms, cx.ev[0], cx.ev[1]));
 }
 
 // Fr NTT (scope row 8f.2).  src / tgt may be host or device memory (device: the transform can feed
@@ -1259,11 +1277,14 @@ void run_ntt(int m, const uint64_t* gen, const uint64_t* src, int src_loc, uint6
     d_src = p;
   }
   g_launches += 1 + (m + 8) / 9;
+  CK(cudaEventRecord(cx.ev[0], s));
   ntt_device<F>(s, m, d_gen, d_src, d_tmp, d_dst, d_table, inverse);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(cx.ev[1], s));
   if (tgt_loc != ZKB200_DEVICE) CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
   else if ((void*)d_dst != (void*)tgt) CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToDevice, s));
   CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(&cx.last_op_ms, cx.ev[0], cx.ev[1]));
 }
 
 // FFT of G1 group elements (scope row 8f.4): host buffers in, host buffers out
@@ -1284,10 +1305,13 @@ void run_gfft(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, in
   CK(cudaMemcpyAsync(d_gen, gen, 32, cudaMemcpyHostToDevice, s));
   host_to_device(cx, d_src, src, bytes, s);
   g_launches += 3 + m;
+  CK(cudaEventRecord(cx.ev[0], s));
   gfft_device<C>(s, m, d_gen, d_src, d_work, d_table, d_dst, inverse, jac);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(cx.ev[1], s));
   CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(&cx.last_op_ms, cx.ev[0], cx.ev[1]));
 }
 
 }  // namespace
@@ -1369,6 +1393,12 @@ void zkb200_srs_cache_drop(void) {
     std::lock_guard<std::mutex> lk(cx.mu);
     cx.srs_drop_all();
   }
+}
+
+float zkb200_last_op_ms(void) {
+  DeviceCtx& cx = get_ctx();
+  std::lock_guard<std::mutex> lk(cx.mu);
+  return cx.last_op_ms;
 }
 
 int zkb200_last_srs_hit(void) {
