@@ -2,7 +2,7 @@
 """bench.py -- G1 MSM throughput on B200 (BASELINE.json metric), one JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config bls20|bn20|bn24|bls26|kzg] [--impl ours|reference]
-                    [--in-library-devices] [--no-cpu-baseline] [--window C]
+                    [--in-library-devices] [--no-cpu-baseline] [--window C] [--row f1|f2|f3|f4]
     (aliases: --scaling strong --global-logn 24 --curve bn128  ==  --config bn24, and so on)
 
 A "step" is one complete pass of the hot path over one batch of synthetic input (tests/workloads.py):
@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--global-logn", type=int, default=None, help="log2(points in total), strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--row", default=None, choices=["f1", "f2", "f3", "f4"],
+                    help="one of the 'next' rows of the scope table instead of the MSM (tools/bench_rows.py), one GPU")
     ap.add_argument("--in-library-devices", action="store_true",
                     help="one process, the library shards the host arrays over --gpus devices itself (ZKB200_DEVICES path)")
     a = ap.parse_args()
@@ -284,6 +286,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    if args.row:
+        if rank != 0:
+            return
+        from zikkurat_algebra_b200 import build as zkbuild
+        zkbuild.build()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_rows
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        line = bench_rows.run(args.row, args.steps, args.warmup, sampler, want_cpu=not args.no_cpu_baseline)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
+        return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
