@@ -182,6 +182,17 @@ int zkb200_last_srs_hit(void);
 /* forget every resident point array on every device (the next call over an array uploads it again) */
 void zkb200_srs_cache_drop(void);
 
+/* Endomorphism (GLV) split of the scalars, on by default ($ZKB200_GLV=0 or zkb200_set_glv(0) switch it off): every scalar
+ * longer than 160 bits is split as k = k1 + k2*lambda (mod r) with 127-bit halves and the MSM runs over the 2n points
+ * P_i, phi(P_i), phi(x, y) = (beta*x, y) -- half the windows for the same number of bucket insertions.
+ * PRECONDITION that the reference does not have: phi(P) = lambda*P holds for points of the prime-order subgroup only.
+ * BN254 G1 has cofactor 1, so every point on the curve qualifies; BLS12-381 G1 has cofactor 0x396c8c005555e1568c00aaab0000aaab,
+ * so a caller that feeds curve points OUTSIDE the subgroup (the reference multiplies them by the integer scalar like
+ * any other point: it validates nothing) must switch the split off to get the reference's answer.
+ * G1 elements of an SRS, commitments, proofs -- everything a KZG prover handles -- are subgroup points.
+ * tests/test_configs_gpu.py::test_glv_precondition_and_switch shows both sides. */
+void zkb200_set_glv(int on);
+
 /* Give back all device memory this library holds on every device it has used (work arrays that only grow otherwise,
  * the pinned result buffer, the resident point arrays).  The next call allocates again.  A work-array allocation
  * that fails first drops the resident point arrays and retries; batches that would not fit are processed in halves;

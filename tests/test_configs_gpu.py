@@ -178,3 +178,45 @@ def test_in_library_multi_gpu_matches_golden(zk):
         assert got.tobytes() == workloads.golden_bytes(k["curve"], 1 << k["logn"], k["form"], k["seed"], k["nmsm"])
     finally:
         zk.set_devices([])
+
+
+def test_glv_precondition_and_switch(zk):
+    """The endomorphism split assumes points of the prime-order subgroup.  BN254 G1 has cofactor 1 (nothing to assume);
+    BLS12-381 G1 has curve points outside the subgroup, which the reference multiplies like any other point
+    (it validates nothing: lib/cbits/curves/g1/proj/bn128_G1_proj.c:549-561).  With the split OFF the library reproduces
+    the reference for such inputs bit for bit; with it ON it reproduces the reference for subgroup points (every other test)."""
+    from tests import pyec
+    curve = "bls12_381"
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    # curve points with small x: on y^2 = x^3 + 4 but (with overwhelming probability) not in the subgroup of order r
+    pts = []
+    x = 1
+    while len(pts) < 64:
+        x += 1
+        rhs = (x * x * x + 4) % cv.p
+        y = pow(rhs, (cv.p + 1) // 4, cv.p)          # p = 3 mod 4
+        if y * y % cv.p == rhs:
+            pts.append((x, y))
+    assert any(cv.mul(cv.r, P) is not None for P in pts[:4])          # really outside the subgroup
+    arr = np.frombuffer(cv.points_to_bytes(pts), dtype=np.uint64).copy().reshape(len(pts), 2 * L)
+    sc = refs.counter_scalars(91, 0, len(pts))
+    lib, pre = (refs.ref(), "") if refs.have_ref() else (refs.oracle(), "zko_")
+    sym = f"{curve}_G1_proj_MSM_std_coeff_affine_out"
+    want = refs.call_msm(lib, pre + sym, sc.ravel(), arr.ravel(), 2 * L, n=len(pts))
+    try:
+        zk.set_glv(False)
+        got_off = zk.call_reference_symbol(sym, sc, arr)
+    finally:
+        zk.set_glv(True)
+    assert got_off.tobytes() == want.tobytes()
+    # subgroup points: identical with and without the split
+    sub = refs.chain_points(curve, 64, s0=5, s1=9)
+    want = refs.call_msm(lib, pre + sym, sc.ravel(), sub.ravel(), 2 * L, n=64)
+    on = zk.call_reference_symbol(sym, sc, sub)
+    try:
+        zk.set_glv(False)
+        off = zk.call_reference_symbol(sym, sc, sub)
+    finally:
+        zk.set_glv(True)
+    assert on.tobytes() == off.tobytes() == want.tobytes()

@@ -21,7 +21,7 @@ import numpy as np
 __all__ = [
     "CURVES", "lib", "lib_path", "msm", "msm_std", "msm_batch", "msm_device", "sum_points", "batch_to_affine", "batch_from_affine", "CONVERT_SYMBOLS", "ntt", "ntt_device", "NTT_SYMBOLS", "G2_SYMBOLS", "GFFT_SYMBOLS", "EXTRA_SYMBOLS", "group_fft", "call_reference_symbol",
     "last_stats", "imad_peak", "set_device", "set_devices", "gen_chain", "launch_count", "ResidentPoints", "REFERENCE_SYMBOLS", "EXTENSION_SYMBOLS",
-    "msm_to_device", "sum_points_device", "last_srs_hit", "release_workspaces", "srs_cache_drop", "last_op_ms", "selftest_field", "selftest_group", "FIELD_OPS", "GROUP_OPS",
+    "msm_to_device", "sum_points_device", "last_srs_hit", "release_workspaces", "srs_cache_drop", "last_op_ms", "set_glv", "selftest_field", "selftest_group", "FIELD_OPS", "GROUP_OPS",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -52,7 +52,7 @@ EXTRA_SYMBOLS = ([f"{c}_G2_proj_batch_{d}_affine" for c in ("bn128", "bls12_381"
 EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zkb200_last_stats", "zkb200_imad_peak",
                      "zkb200_version", "zkb200_gen_chain", "zkb200_launch_count", "zkb200_set_devices", "zkb200_ntt", "zkb200_device_upload", "zkb200_device_free", "zkb200_last_affine_levels",
                      "zkb200_msm_ex", "zkb200_sum_points_ex", "zkb200_last_srs_hit", "zkb200_srs_cache_drop", "zkb200_release_workspaces",
-                     "zkb200_selftest_field", "zkb200_selftest_group", "zkb200_last_op_ms"]
+                     "zkb200_selftest_field", "zkb200_selftest_group", "zkb200_last_op_ms", "zkb200_set_glv"]
 FIELD_IDS = {("bn128", "Fp"): 0, ("bls12_381", "Fp"): 1, ("bn128", "Fr"): 2, ("bls12_381", "Fr"): 3}
 FIELD_OPS = {"mul": 0, "sqr": 1, "mul2": 2, "add": 3, "sub": 4, "neg": 5, "inv": 6, "mul_call": 7, "sqr_call": 8, "mul2_call": 9,
              "dbl": 10, "from_mont": 11}
@@ -252,6 +252,14 @@ def last_srs_hit() -> bool:
 
 def release_workspaces() -> None:
     lib().zkb200_release_workspaces()
+
+
+def set_glv(on: bool) -> None:
+    """Switch the endomorphism (GLV) split of the scalars on / off (see zkb200_set_glv: subgroup precondition)."""
+    L = lib()
+    L.zkb200_set_glv.argtypes = [ctypes.c_int]
+    L.zkb200_set_glv.restype = None
+    L.zkb200_set_glv(int(bool(on)))
 
 
 def last_op_ms() -> float:

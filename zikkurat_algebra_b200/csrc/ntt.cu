@@ -9,7 +9,7 @@
 // Algorithm: decimation in time.  The bit reversal is folded into the first pass's gather (one 32-byte
 // element = one DRAM sector, so element-granular scatter/gather costs no extra traffic); every pass stages a
 // tile of 512 elements in shared memory and runs up to 9 butterfly stages on it, one butterfly per thread and
-// stage.  Twiddles come from a table w^i, i < N/2, built on the device (cached per (gen, m)); the inverse uses
+// stage.  Twiddles come from a table w^i, i < N/2, built on the device at the start of every call (one kernel, N/2 Fr multiplications: about the cost of one butterfly pass; not cached across calls); the inverse uses
 // w^-i = -w^(N/2-i) from the same table and multiplies by N^-1 = (1/2)^m in its last pass.
 // HBM traffic: ceil(m/9) passes x 64 B per element (+ table reads); 1 Fr multiplication per butterfly.
 #include <cuda_runtime.h>

@@ -150,6 +150,18 @@ std::atomic<long long> g_launches{0};  // kernels launched by this library since
 
 std::vector<int> device_list();
 
+// GLV split on/off: zkb200_set_glv, else $ZKB200_GLV, else on
+std::atomic<int> g_glv{-1};
+bool glv_enabled() {
+  int v = g_glv.load();
+  if (v < 0) {
+    const char* e = getenv("ZKB200_GLV");
+    v = e ? (atoi(e) != 0) : 1;
+    g_glv.store(v);
+  }
+  return v != 0;
+}
+
 // The ONE place that decides which GPU a call without an explicit device runs on: zkb200_set_device, else a
 // one-element device list (zkb200_set_devices / $ZKB200_DEVICES="2"), else $ZKB200_DEVICE, else 0.  Uploads
 // (zkb200_device_upload), statistics and MSM calls therefore always agree.
@@ -450,8 +462,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
   int nbits = mont ? C::Fr::BITS : 64 * nl;
   // GLV split (glv.cuh): 2n points (P_i, phi(P_i)) with 127-bit scalars -> half the windows.  Only for scalars that are
   // longer than the split halves in the first place ($ZKB200_GLV=0 switches it off).
-  static const bool glv_on = [] { const char* e = getenv("ZKB200_GLV"); return e ? atoi(e) != 0 : true; }();
-  const bool glv = GlvOf<C>::available && glv_on && nbits > 160 && n > 0;
+  const bool glv = GlvOf<C>::available && glv_enabled() && nbits > 160 && n > 0;
   const size_t F = glv ? 2 : 1;        // pairs per point and window
   if (glv) nbits = 127;
   int c = 0, W = 0, K = 1;
@@ -1394,6 +1405,8 @@ void zkb200_srs_cache_drop(void) {
     cx.srs_drop_all();
   }
 }
+
+void zkb200_set_glv(int on) { g_glv.store(on ? 1 : 0); }
 
 float zkb200_last_op_ms(void) {
   DeviceCtx& cx = get_ctx();
