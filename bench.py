@@ -11,6 +11,7 @@ A "step" is one complete pass of the hot path over one batch of synthetic input 
   bls20    [1] BLS12-381 G1 MSM 2^20 (DEFAULT; the headline)               weak: 2^20 points per GPU
   bn20     [0] BN254 G1 MSM (2^20 on the GPU)                              weak
   bn24     [2] BN254 G1 MSM 2^24 sharded across 2/4/8 GPUs                 strong: 2^24 points in total
+  bls24    (north_star's target size, BLS12-381 twin of [2])               strong: 2^24 points in total
   bls26    [3] BLS12-381 G1 MSM 2^26 sharded across 8 GPUs (std scalars)   strong
   kzg      [4] 256 x BN254 G1 MSM of 2^14 over one shared SRS              strong: whole MSMs dealt to the GPUs
 
@@ -60,7 +61,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default=None, choices=["bls20", "bn20", "bn24", "bls26", "kzg"])
+    ap.add_argument("--config", default=None, choices=["bls20", "bn20", "bn24", "bls24", "bls26", "kzg"])
     ap.add_argument("--curve", default=None, choices=["bls12_381", "bn128"])
     ap.add_argument("--logn", type=int, default=None, help="log2(points per GPU), weak scaling")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
@@ -77,7 +78,7 @@ def parse():
         # aliases: (--curve, --logn) weak, or (--scaling strong, --global-logn, --curve)
         if a.scaling == "strong" or a.global_logn is not None:
             want = (a.curve or "bn128", a.global_logn or 24)
-            a.config = {("bn128", 24): "bn24", ("bls12_381", 26): "bls26"}.get(want)
+            a.config = {("bn128", 24): "bn24", ("bls12_381", 24): "bls24", ("bls12_381", 26): "bls26"}.get(want)
             if a.config is None:
                 a.custom = dict(curve=want[0], logn=want[1], form="mont", seed=3 if want[0] == "bn128" else 2, weak=False, nmsm=1,
                                 title=f"{want[0]} G1 MSM, 2^{want[1]} points in total")

@@ -29,6 +29,9 @@ CONFIGS = {
     # configs[2]: BN254 G1 MSM 2^24 sharded across 2/4/8 B200 (strong scaling)
     "bn24": dict(curve="bn128", logn=24, form="mont", seed=3, weak=False, nmsm=1,
                  title="BN254 G1 MSM, 2^24 points in total"),
+    # north_star's target size for both curves: 2^24 points on 8 GPUs (BN254 is config 3; this is the BLS12-381 twin)
+    "bls24": dict(curve="bls12_381", logn=24, form="mont", seed=2, weak=False, nmsm=1,
+                  title="BLS12-381 G1 MSM, 2^24 points in total"),
     # configs[3]: BLS12-381 G1 MSM 2^26 sharded across 8 B200; standard-form scalars (the reference's mont entry
     # point overflows `int` in malloc(8*expo_nlimbs*npoints) at 2^26, lib/cbits/curves/g1/proj/bn128_G1_proj.c:630)
     "bls26": dict(curve="bls12_381", logn=26, form="std", seed=4, weak=False, nmsm=1,

@@ -251,6 +251,29 @@ bool host_is_pinned(const void* p) {
   return false;
 }
 
+// Copy into the pinned ring with streaming (non-temporal) stores: the destination is written once and read by the
+// DMA engine only, so it should neither be read for ownership nor displace the caller's data from the caches --
+// with 8 processes staging at once the host's memory bandwidth is the limit (profiles/r2_notes.md).  dst is 64-byte
+// aligned (ring slots are multiples of 2 MiB inside a page-aligned allocation); src has the caller's alignment.
+#if defined(__x86_64__) && defined(__SSE2__)
+#include <emmintrin.h>
+inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+  size_t i = 0;
+  for (; i + 64 <= n; i += 64) {
+    const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+    const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+    _mm_stream_si128((__m128i*)(dst + i), a);
+    _mm_stream_si128((__m128i*)(dst + i + 16), b);
+    _mm_stream_si128((__m128i*)(dst + i + 32), c);
+    _mm_stream_si128((__m128i*)(dst + i + 48), d);
+  }
+  if (i < n) memcpy(dst + i, src + i, n - i);
+  _mm_sfence();      // the stores are globally visible before the DMA is queued
+}
+#else
+inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) { memcpy(dst, src, n); }
+#endif
+
 // Persistent staging threads (created on the first pageable copy of a device, never joined: they sleep on a condition
 // variable between copies).  A job = one host_to_device call; worker w stages chunks w, w+T, ... into its ring slots.
 struct StagePool {
@@ -299,7 +322,7 @@ struct StagePool {
         const int slot = (int)(i % R);
         if (cx->stage_used[slot]) CK(cudaEventSynchronize(cx->stage_ev[slot]));   // previous DMA out of this slot finished
         const size_t off = i * CH, len = bytes - off < CH ? bytes - off : CH;
-        memcpy(cx->stage + (size_t)slot * CH, src + off, len);
+        stage_copy(cx->stage + (size_t)slot * CH, src + off, len);
         CK(cudaMemcpyAsync(dst + off, cx->stage + (size_t)slot * CH, len, cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(cx->stage_ev[slot], stream));
         cx->stage_used[slot] = true;
