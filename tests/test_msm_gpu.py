@@ -775,6 +775,64 @@ def test_affine_pre_reduction_levels(zk, curve):
         assert np.asarray(outs[i]).tobytes() == w, i
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_reduction_and_handover_switches(zk, curve):
+    """Two code paths behind switches must give the reference's bytes whichever way the switch is set:
+    $ZKB200_RED2D (row / column form of the bucket reduction, kernels_red.cuh K5'; windows narrower than 7 bits always
+    take the level recurrence) and $ZKB200_AFF_NEXT (a tree level hands the next one its denominators,
+    kernels_aff.cuh; needs an even number of merges per segment, so ragged sizes mix both forms)."""
+    cv = pyec.CURVES[curve]
+    pts_all = refs.chain_points(curve, 6001)
+    n = 3000
+    pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=11, reduce=False)
+    want = cpu_affine(curve, sc, pts).tobytes()
+    for red in (0, 1):
+        for c in (6, 7, 8, 10, 13, 16):
+            with _Env(ZKB200_RED2D=red):
+                out = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_proj_out_variable", sc, pts, window_size=c)
+            assert to_affine_cpu(curve, "proj", out).tobytes() == want, (red, c)
+        for K in (1, 3):   # input slices: several bucket arrays summed on the fly by the first reduction step
+            with _Env(ZKB200_RED2D=red, ZKB200_SLICES=K):
+                got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
+            assert got.tobytes() == want, (red, K)
+    for n in (64, 256, 1000, 4096, 6001):
+        pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=500 + n, reduce=False)
+        want = cpu_affine(curve, sc, pts).tobytes()
+        for R in (2, 3, 5):
+            for glv in (0, 1):
+                zk.set_glv(glv)
+                try:
+                    with _Env(ZKB200_AFF_NEXT=1, ZKB200_AFFINE=R):
+                        got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
+                finally:
+                    zk.set_glv(1)
+                assert got.tobytes() == want, (n, R, glv)
+    # the hand-over classifies P + P, P - P and infinity operands a level early
+    G = cv.gen
+    P, Q = cv.mul(7, G), cv.mul(1234567, G)
+    sets = {
+        "repeated": ([3] * 16, [P] * 16),
+        "repeated_mixed": ([3, 3, 3, 3, 8, 8, 8, 8], [P, P, Q, Q, Q, P, P, P]),
+        "neg_pairs": ([77] * 8, [P, Q, cv.neg(P), cv.neg(Q), P, cv.neg(P), Q, Q]),
+        "inf_inputs": ([9, 9, 9, 9, 2, 2, 2, 2], [None, P, None, None, Q, None, P, P]),
+        "all_cancel": ([5] * 8, [P, cv.neg(P), Q, cv.neg(Q), P, cv.neg(P), Q, cv.neg(Q)]),
+    }
+    for name, (ks, pl) in sets.items():
+        want = cv.affine_to_bytes(cv.msm(ks, pl))
+        Pb = np.frombuffer(cv.points_to_bytes(pl), dtype=np.uint64).copy()
+        Sm = np.frombuffer(b"".join(cv.scalar_mont_bytes(k) for k in ks), dtype=np.uint64).copy()
+        for R in (2, 3):
+            for c in (0, 3):
+                for glv in (0, 1):
+                    zk.set_glv(glv)
+                    try:
+                        with _Env(ZKB200_AFF_NEXT=1, ZKB200_AFFINE=R, ZKB200_WINDOW=c):
+                            got = zk.call_reference_symbol(f"{curve}_G1_jac_MSM_mont_coeff_affine_out", Sm, Pb)
+                    finally:
+                        zk.set_glv(1)
+                    assert got.tobytes() == want, (name, R, c, glv)
+
+
 def test_affine_pre_reduction_mid_size_vs_threaded_reference(zk):
     curve, n = "bls12_381", 1 << 17
     pts = refs.chain_points(curve, n)

@@ -6,38 +6,43 @@
 // exactly like bn128_G1_proj_normalize, :75-96; the Jacobian and G2 twins normalise the same way:
 // bn128_G1_jac.c:62-85, bn128_G2_proj.c:70-89), hence bit-comparable.
 //
-// Radix-2 decimation in time on XYZZ points held in global memory: one launch per stage, one thread per butterfly
+// Radix-2 decimation in time on XYZZ points held in global memory: one launch per stage, one 4-lane TEAM per butterfly
 // (a, b) -> (a + w*b, a - w*b); w*b is a 4-bit fixed-window scalar multiplication (the reference does the same per
 // butterfly with bn128_G1_proj_scl_Fr_mont).  Twiddles come from the Fr table of ntt.cu (w^-i = -w^(N/2-i)).
 // The work is N/2 * log2 N scalar multiplications (~3 300 Fp multiplications each): IMAD-bound, no data reuse to stage.
+// A stage has only N/2 independent scalar multiplications (8192 at 2^14: a fifth of the GPU's resident threads), each a
+// chain of ~330 dependent group operations, so a butterfly is worked on by the 4 lanes of a team (ec_team.cuh: a
+// doubling is 3 multiplication rounds instead of 9 dependent multiplications, an addition 4 instead of 14).
 #include <cuda_runtime.h>
 
+#include "ec_team.cuh"
 #include "gfft.cuh"
 #include "msm_common.cuh"
 #include "ntt.cuh"
 
 namespace zk {
 
-// one out-of-line copy of each group operation for this translation unit
+// one out-of-line copy of each group operation for this translation unit (team versions: all 4 lanes of a team call
+// them with identical operands)
 template <class P>
-__device__ __noinline__ void gf_add(Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add<P>(a, b); }
+__device__ __noinline__ void gf_add(const Team& tm, Xyzz<P>& a, const Xyzz<P>& b) { a = xyzz_add_team<P>(tm, a, b); }
 template <class P>
-__device__ __noinline__ void gf_dbl(Xyzz<P>& a) { a = xyzz_dbl<P>(a); }
+__device__ __noinline__ void gf_dbl(const Team& tm, Xyzz<P>& a) { a = xyzz_dbl_team<P>(tm, a); }
 
 // k * p for a standard-form 256-bit scalar k (8 x u32), 4-bit fixed windows, table of 1p..15p in local memory
 template <class P>
-__device__ __noinline__ Xyzz<P> xyzz_scalar_mul(const Xyzz<P>& p, const uint32_t* k) {
+__device__ __noinline__ Xyzz<P> xyzz_scalar_mul(const Team& tm, const Xyzz<P>& p, const uint32_t* k) {
   Xyzz<P> tab[15];
   tab[0] = p;
   for (int i = 1; i < 15; i++) {           // tab[i] = (i+1) * p
-    if (i & 1) { tab[i] = tab[i >> 1]; gf_dbl<P>(tab[i]); }
-    else { tab[i] = tab[i - 1]; gf_add<P>(tab[i], p); }
+    if (i & 1) { tab[i] = tab[i >> 1]; gf_dbl<P>(tm, tab[i]); }
+    else { tab[i] = tab[i - 1]; gf_add<P>(tm, tab[i], p); }
   }
   Xyzz<P> acc = xyzz_inf<P>();
   for (int w = 63; w >= 0; w--) {
-    for (int d = 0; d < 4; d++) gf_dbl<P>(acc);   // no-op while acc is infinity
+    for (int d = 0; d < 4; d++) gf_dbl<P>(tm, acc);   // no-op while acc is infinity
     uint32_t dig = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
-    if (dig) gf_add<P>(acc, tab[dig - 1]);
+    if (dig) gf_add<P>(tm, acc, tab[dig - 1]);
   }
   return acc;
 }
@@ -65,9 +70,10 @@ __global__ void __launch_bounds__(128)
 k_gfft_stage(XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restrict__ table, int m, int s, int inverse) {
   using P = typename C::Fp;
   using F = typename C::Fr;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // butterfly of this team
   const size_t half = (size_t)1 << (m - 1);
   if (t >= half) return;
+  const Team tm;
   const size_t j = t & (((size_t)1 << (s - 1)) - 1);
   const size_t ia = ((t >> (s - 1)) << s) + j, ib = ia + ((size_t)1 << (s - 1));
   const size_t idx = j << (m - s);
@@ -78,14 +84,16 @@ k_gfft_stage(XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restr
     for (int k = 0; k < 8; k++) w.l[k] = tw[k];
     if (inverse) w = fe_neg<F>(w);                 // w^-idx = -w^(N/2 - idx)
     w = fe_from_mont<F>(w);                        // plain integer for the scalar multiplication
-    b = xyzz_scalar_mul<P>(b, w.l);
+    b = xyzz_scalar_mul<P>(tm, b, w.l);
   }
   Xyzz<P> nb = b;
   nb.Y = fe_neg<P>(b.Y);
-  gf_add<P>(nb, a);
-  gf_add<P>(a, b);
-  store_xyzz<P>(data + ia, a);
-  store_xyzz<P>(data + ib, nb);
+  gf_add<P>(tm, nb, a);
+  gf_add<P>(tm, a, b);
+  if (tm.t == 0) {
+    store_xyzz<P>(data + ia, a);
+    store_xyzz<P>(data + ib, nb);
+  }
 }
 
 // optional scaling by N^-1 (inverse transform), then normalised projective output
@@ -96,16 +104,18 @@ k_gfft_store(const XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* _
   using P = typename C::Fp;
   using F = typename C::Fr;
   constexpr int L = P::L;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // one team per point
   if (i >= ((size_t)1 << m)) return;
+  const Team tm;
   Xyzz<P> a = load_xyzz<P>(data + i);
   if (scale && m > 0) {
     Fe<F> ninv;
     const uint32_t* q = table + ((size_t)1 << (m - 1)) * 8;
     for (int k = 0; k < 8; k++) ninv.l[k] = q[k];
     ninv = fe_from_mont<F>(ninv);
-    a = xyzz_scalar_mul<P>(a, ninv.l);
+    a = xyzz_scalar_mul<P>(tm, a, ninv.l);
   }
+  if (tm.t != 0) return;
   uint32_t* o = dst + i * 3 * L;
   Affine<P> aff;
   if (xyzz_to_affine<P>(a, aff)) {
@@ -124,8 +134,8 @@ void gfft_device(cudaStream_t s, int m, const uint32_t* d_gen, const uint32_t* d
   ntt_build_table<typename C::Fr>(s, d_gen, N >> 1, m, d_table);
   k_gfft_load<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(d_src, m, jac, data);
   for (int st = 1; st <= m; st++)
-    k_gfft_stage<C><<<(unsigned)(((N >> 1) + 127) / 128), 128, 0, s>>>(data, d_table, m, st, inverse);
-  k_gfft_store<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(data, d_table, m, inverse, d_dst);
+    k_gfft_stage<C><<<(unsigned)((4 * (N >> 1) + 127) / 128), 128, 0, s>>>(data, d_table, m, st, inverse);
+  k_gfft_store<C><<<(unsigned)((4 * N + 127) / 128), 128, 0, s>>>(data, d_table, m, inverse, d_dst);
 }
 
 template void gfft_device<Bn254>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);

@@ -13,6 +13,12 @@
 //   batch_invert  inverts all thread totals: a few tiny kernels (warp-scan product trees, one fe_inv at the top)
 //   k_aff_add     walks the same merges backwards, peels 1/d off the inverted total, finishes the additions,
 //                 writes the sums to the temporary point array and the merged block states for the next level
+// From level 1 on the denominators are already known when the level below finishes: merge m' of level r+1 adds the
+// tail of block 2m' and the head of block 2m'+1, which two NEIGHBOURING lanes of level r's k_aff_add have just produced.
+// The even lane therefore forms d' = x2 - x1 from registers (one shuffle of the partner's x; operands that are older
+// partial sums are fetched) and stores it where level r+1 expects its running products; level r+1's first step then is
+// k_aff_prefix, an in-place exclusive prefix product over that array -- coalesced, no gather, no classification --
+// instead of k_aff_prod's second gather of every operand's x coordinate.
 // After R levels the 2 * ceil(n / 2^R) surviving (key, ref) records per segment go through the ordinary
 // k_accumulate / fix-up path; runs that were closed inside a block were already written to their buckets.
 // P+P, P+(-P) and infinity operands are classified per merge and keep their exact group-law meaning.
@@ -47,6 +53,14 @@ ZK_D void st_fe(uint32_t* p, const Fe<P>& v) {
   uint4* q = reinterpret_cast<uint4*>(p);
 #pragma unroll
   for (int k = 0; k < P::L / 4; k++) q[k] = make_uint4(v.l[4 * k], v.l[4 * k + 1], v.l[4 * k + 2], v.l[4 * k + 3]);
+}
+
+template <class P>
+ZK_D Fe<P> shfl_fe(const Fe<P>& v, int delta, bool up) {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < P::L; i++) r.l[i] = up ? __shfl_up_sync(0xffffffffu, v.l[i], delta) : __shfl_down_sync(0xffffffffu, v.l[i], delta);
+  return r;
 }
 
 template <class P>
@@ -144,27 +158,61 @@ k_aff_prod(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
   st_fe<P>(tot + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L, run);
 }
 
+// ---- step 1 for levels whose denominators were handed down by the level below (k_aff_add<NEXT>) ----------------
+// pre[m] holds d_m (ONE where merge m adds nothing); it is replaced by the product of this thread's earlier d's.
+template <class P>
+__global__ void __launch_bounds__(AFF_THREADS)
+k_aff_prefix(uint32_t total, uint32_t* __restrict__ pre, uint32_t* __restrict__ tot, int B) {
+  constexpr bool CALLS = (P::L > 8);
+  const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * B);
+  Fe<P> run = fe_one<P>();
+  uint32_t m = tile + threadIdx.x;
+  Fe<P> d = m < total ? ld_fe<P>(pre + (size_t)m * P::L) : fe_one<P>();
+#pragma unroll 1
+  for (int j = 0; j < B; j++, m += AFF_THREADS) {
+    if (m >= total) break;
+    const uint32_t mn = m + AFF_THREADS;
+    Fe<P> dn = (j + 1 < B && mn < total) ? ld_fe<P>(pre + (size_t)mn * P::L) : fe_one<P>();   // next load under this product
+    st_fe<P>(pre + (size_t)m * P::L, run);
+    run = aff_mul<P, CALLS>(run, d);
+    d = dn;
+  }
+  st_fe<P>(tot + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L, run);
+}
+
 // ---- step 3: finish the additions, write sums and merged states ---------------------------------------------
 // totinv[t] = inverse of thread t's total.  Sums go to tmp[tmp_off + m].  Output: st_out[m] (uint4 states) or,
 // on the LAST level, split (key, ref) records for k_accumulate: 2 per block, head slot 0 when the block is one run.
 // The operands of merge j-1 (two points and the stored running product, 5 x field element) travel into this
 // thread's shared-memory slot with cp.async while merge j is being computed, exactly like the point gather of
 // k_accumulate.  Slot layout [buffer][16-byte word][thread]: conflict-free.
+// Build-time experiment switches (tools/build_variant.py): resident blocks per SM asked of ptxas for k_aff_add, and
+// whether the stored running product travels through the shared-memory slot too (it costs a fifth of the slot).
+#ifndef ZK_AFF_MINB
+#define ZK_AFF_MINB 1
+#endif
+#ifndef ZK_AFF_STAGE_PRE
+#define ZK_AFF_STAGE_PRE 1
+#endif
 template <class P>
-constexpr bool aff_stage_pre() { return P::L <= 16; }   // 24 limbs (BLS12-381 Fp2): the points alone fill the slot
+__host__ __device__ constexpr bool aff_stage_pre() { return ZK_AFF_STAGE_PRE && P::L <= 16; }   // 24 limbs (BLS12-381 Fp2): the points alone fill the slot
 template <class P>
 constexpr int aff_stage_words() { return 2 * ((2 * P::L) / 4) + (aff_stage_pre<P>() ? P::L / 4 : 0); }
 template <class P>
 constexpr size_t aff_stage_bytes() { return (size_t)2 * aff_stage_words<P>() * AFF_THREADS * 16; }
 
-template <class C, bool LEVEL0, bool LAST, bool CALLS>
-__global__ void __launch_bounds__(AFF_THREADS)
+// NEXT: also hand the next level its denominators (dnext[m / 2], see the header); needs an even number of merges per
+// segment so that the two blocks of a next-level merge sit in neighbouring lanes.
+template <class C, bool LEVEL0, bool LAST, bool CALLS, bool NEXT>
+__global__ void __launch_bounds__(AFF_THREADS, ZK_AFF_MINB)
 k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
           uint32_t nm, uint32_t total, const uint32_t* points, int pstride, uint32_t* tmp, uint32_t tmp_off, const uint32_t* __restrict__ pre,
           const uint32_t* __restrict__ totinv, uint4* __restrict__ st_out, uint32_t* __restrict__ keys_out,
-          uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets, int B) {
+          uint32_t* __restrict__ vals_out, uint32_t NB, XyzzMem<typename C::Fp>* __restrict__ buckets, int B,
+          uint32_t* __restrict__ dnext) {
+  static_assert(!(LAST && NEXT), "the last level has no successor");
   using P = typename C::Fp;
-  constexpr bool SPRE = (P::L <= 16);
+  constexpr bool SPRE = aff_stage_pre<P>();
   constexpr int PW = (2 * P::L) / 4, FW = SPRE ? P::L / 4 : 0, NW = 2 * PW + FW;
   extern __shared__ uint4 aff_stage[];   // [2][NW][AFF_THREADS]
   const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * B);
@@ -207,8 +255,13 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
     const bool have_next = fetch(j - 1, (j - 1) & 1, an, segn, in_);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
+    // what the next level needs from this merge (NEXT): the merged block and, if it was formed, the new sum
+    uint32_t o_hk = 0, o_hr = 0, o_tk = 0, o_tr = 0, o_sref = 0;
+    bool o_add = false, o_sinf = false;
+    Affine<P> o_s;
+    if constexpr (NEXT) { o_s.x = fe_zero<P>(); o_s.y = fe_zero<P>(); }
     if (have) {
-      const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
       AffPlan pl = aff_plan(a.Lhk, a.Lhr, a.Ltk, a.Ltr, a.Rhk, a.Rhr, a.Rtk, a.Rtr);
       XyzzMem<P>* bseg = buckets + (size_t)seg * NB;
       if (pl.add) {
@@ -246,6 +299,7 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
         const uint32_t sref = AFF_TEMP | (tmp_off + m);
         if (pl.hr == AFF_SUM) pl.hr = sref;
         if (pl.tr == AFF_SUM) pl.tr = sref;
+        if constexpr (NEXT) { o_add = true; o_sref = sref; o_s = s; o_sinf = sinf; }
       } else {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -265,6 +319,41 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
       } else {
         st_out[m] = make_uint4(pl.hk, pl.hr, pl.tk, pl.tr);
       }
+      if constexpr (NEXT) { o_hk = pl.hk; o_hr = pl.hr; o_tk = pl.tk; o_tr = pl.tr; }
+    }
+    if constexpr (NEXT) {
+      // Lanes 2q and 2q+1 hold the left and the right block of next-level merge m / 2 (tile and nm are even).  The even
+      // lane needs the partner's head: key, ref, and the x coordinate when that head is the sum just formed.
+      const bool odd = (threadIdx.x & 1) != 0;
+      const uint32_t ek = have ? (odd ? o_hk : o_tk) : 0u;      // the run facing the partner
+      const uint32_t er = odd ? o_hr : o_tr;
+      const bool e_sum = o_add && er == o_sref;
+      const uint32_t rk = __shfl_down_sync(0xffffffffu, ek, 1);
+      const uint32_t rr = __shfl_down_sync(0xffffffffu, er, 1);
+      const int rfl = __shfl_down_sync(0xffffffffu, (e_sum ? 1 : 0) | (o_sinf ? 2 : 0), 1);
+      const Fe<P> rx = shfl_fe<P>(o_s.x, 1, false);
+      Fe<P> dn = fe_one<P>();
+      bool exc = false;
+      if (!odd && have && ek == rk && ek != 0) {
+        Fe<P> x1 = e_sum ? o_s.x : ld_fe<P>(aff_addr<P>(points, pstride, tmp, er));
+        Fe<P> x2 = (rfl & 1) ? rx : ld_fe<P>(aff_addr<P>(points, pstride, tmp, rr));
+        const bool i1 = e_sum ? o_sinf : x1.l[P::L - 1] == 0xffffffffu;
+        const bool i2 = (rfl & 1) ? (rfl & 2) != 0 : x2.l[P::L - 1] == 0xffffffffu;
+        if (i1 || i2 || fe_eq<P>(x1, x2)) exc = true;    // infinity, P + P, P - P: full points below
+        else dn = fe_sub<P>(x2, x1);
+      }
+      if (__any_sync(0xffffffffu, exc)) {
+        const Fe<P> ry = shfl_fe<P>(o_s.y, 1, false);
+        if (exc) {
+          Affine<P> p1, p2;
+          bool j1, j2;
+          if (e_sum) { p1 = o_s; j1 = o_sinf; } else p1 = aff_load<P>(points, pstride, tmp, er, j1);
+          if (rfl & 1) { p2.x = rx; p2.y = ry; j2 = (rfl & 2) != 0; } else p2 = aff_load<P>(points, pstride, tmp, rr, j2);
+          Fe<P> d2;
+          if (aff_classify<P>(p1, j1, p2, j2, d2) >= AFF_ADD) dn = d2;
+        }
+      }
+      if (!odd && have) st_fe<P>(dnext + (size_t)(m >> 1) * P::L, dn);
     }
     have = have_next; a = an; seg = segn; i = in_;
   }
@@ -275,13 +364,6 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
 // One tree level: every thread multiplies BINV_G consecutive elements (exclusive prefixes to PRE), the warp
 // multiplies its 32 thread totals with two shuffle scans; X[t] = product of the OTHER lanes' totals, so that
 // 1/total_t = X[t] / warp_total.  Warp totals form the next level's elements.
-template <class P>
-ZK_D Fe<P> shfl_fe(const Fe<P>& v, int delta, bool up) {
-  Fe<P> r;
-#pragma unroll
-  for (int i = 0; i < P::L; i++) r.l[i] = up ? __shfl_up_sync(0xffffffffu, v.l[i], delta) : __shfl_down_sync(0xffffffffu, v.l[i], delta);
-  return r;
-}
 template <class P>
 ZK_D void binv_warp_products(const Fe<P>& mine, Fe<P>& others, Fe<P>& all) {
   constexpr bool CALLS = (P::L > 8);
@@ -634,6 +716,17 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     return AFF_B;
   };
   uint32_t* inv[2] = {nullptr, nullptr};
+  // Running products of level r live in w.pre (even r) or w.pre2 (odd r): level r's additions read theirs while they
+  // write the next level's denominators into the other array.
+  // Measured (profiles/r2_notes.md section 10): the prefix kernels save 0.13 ms of serialised kernel time per BLS12-381
+  // 2^20 MSM but the additions grow by 0.22 ms (shuffles, a second classification, a fetch for every operand that is not
+  // the new sum), so the hand-over is opt-in ($ZKB200_AFF_NEXT=1; read per call so that the tests can switch it).
+  const bool next_on = [] { const char* e = getenv("ZKB200_AFF_NEXT"); return e ? atoi(e) != 0 : false; }();
+  bool next_l[16];   // level r hands level r+1 its denominators
+  for (int r = 0; r < R; r++) next_l[r] = next_on && r + 1 < R && (nm_l[r] % 2 == 0);
+  auto pre_of = [&](int g, int r) -> uint32_t* {
+    return (r & 1) ? w.pre2 + (size_t)seg0[g] * nm_l[1] * P::L : w.pre + (size_t)seg0[g] * nm_l[0] * P::L;
+  };
   // step 1 + 2 of level r for group g: running products on the group's stream, inversion chain on its chain stream
   auto do_prod = [&](int g, int r) {
     const uint32_t nin = nin_l[r], nm = nm_l[r], total = (uint32_t)segs[g] * nm;
@@ -642,10 +735,11 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     const uint32_t* kg = keys + (size_t)seg0[g] * n;
     const uint32_t* vg = vals + (size_t)seg0[g] * n;
     const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * st_stride[(r - 1) & 1];
-    uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
+    uint32_t* pre = pre_of(g, r);
     uint32_t* tot = w.binv + binv_base[g] * P::L;
     const size_t T0 = (size_t)blocks * AFF_THREADS;
     if (r == 0) k_aff_prod<C, true><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, pre, tot, B);
+    else if (next_l[r - 1]) k_aff_prefix<P><<<blocks, AFF_THREADS, 0, big[g]>>>(total, pre, tot, B);
     else k_aff_prod<C, false><<<blocks, AFF_THREADS, 0, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, pre, tot, B);
     launches++;
     if (big[g] != chain[g]) { ZK_AFF_CK(cudaEventRecord(ln.ev_a[g], big[g])); ZK_AFF_CK(cudaStreamWaitEvent(chain[g], ln.ev_a[g], 0)); }
@@ -662,27 +756,30 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
     const uint32_t* vg = vals + (size_t)seg0[g] * n;
     const uint4* st_in = r == 0 ? nullptr : w.st[(r - 1) & 1] + (size_t)seg0[g] * st_stride[(r - 1) & 1];
     uint4* st_out = w.st[r & 1] + (size_t)seg0[g] * st_stride[r & 1];
-    uint32_t* pre = w.pre + (size_t)seg0[g] * ((n + 1) / 2) * P::L;
+    uint32_t* pre = pre_of(g, r);
+    uint32_t* dnext = next_l[r] ? pre_of(g, r + 1) : nullptr;
     uint32_t* ko = w.keys_out + (size_t)seg0[g] * 2 * nm;
     uint32_t* vo = w.vals_out + (size_t)seg0[g] * 2 * nm;
     XyzzMem<P>* bg = buckets + (size_t)seg0[g] * NB;
     const uint32_t tmp_off = (uint32_t)lvl_off[g];
-#define ZK_AFF_ADD(L0, LA)                                                                                                    \
+#define ZK_AFF_ADD(L0, LA, NX)                                                                                                \
   do {                                                                                                                        \
     if (inl) {                                                                                                                \
-      aff_allow_smem(k_aff_add<C, L0, LA, false>, smem);                                                                      \
-      k_aff_add<C, L0, LA, false><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, tmp_off, \
-                                                                         pre, inv[g], st_out, ko, vo, NB, bg, B);             \
+      aff_allow_smem(k_aff_add<C, L0, LA, false, NX>, smem);                                                                  \
+      k_aff_add<C, L0, LA, false, NX><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp,   \
+                                                                             tmp_off, pre, inv[g], st_out, ko, vo, NB, bg, B, dnext); \
     } else {                                                                                                                  \
-      aff_allow_smem(k_aff_add<C, L0, LA, true>, smem);                                                                       \
-      k_aff_add<C, L0, LA, true><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp, tmp_off,  \
-                                                                        pre, inv[g], st_out, ko, vo, NB, bg, B);              \
+      aff_allow_smem(k_aff_add<C, L0, LA, true, NX>, smem);                                                                   \
+      k_aff_add<C, L0, LA, true, NX><<<blocks, AFF_THREADS, smem, big[g]>>>(kg, vg, st_in, nin, nm, total, points, pstride, w.tmp,    \
+                                                                            tmp_off, pre, inv[g], st_out, ko, vo, NB, bg, B, dnext);  \
     }                                                                                                                         \
   } while (0)
-    if (r == 0 && last) ZK_AFF_ADD(true, true);
-    else if (r == 0) ZK_AFF_ADD(true, false);
-    else if (last) ZK_AFF_ADD(false, true);
-    else ZK_AFF_ADD(false, false);
+    if (r == 0 && last) ZK_AFF_ADD(true, true, false);
+    else if (r == 0 && next_l[r]) ZK_AFF_ADD(true, false, true);
+    else if (r == 0) ZK_AFF_ADD(true, false, false);
+    else if (last) ZK_AFF_ADD(false, true, false);
+    else if (next_l[r]) ZK_AFF_ADD(false, false, true);
+    else ZK_AFF_ADD(false, false, false);
 #undef ZK_AFF_ADD
     launches++;
     lvl_off[g] += total;

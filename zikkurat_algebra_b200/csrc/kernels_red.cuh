@@ -139,6 +139,151 @@ k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typ
   }
 }
 
+// ---- K5', the low-latency form of the bucket reduction (used where a caller waits for it: single MSMs) -------------
+// The level recurrence above is m + 1 + log2(m) dependent group operations per level, and its upper levels are tiny:
+// five launches of ~65 us each that nothing can fill.  Here the NB = 2^(c-1) buckets of a window are seen as a
+// 2^hr x 2^hc matrix (bucket k = k1 * 2^hc + k0):
+//     sum_k (k+1) B_k  =  2^hc * sum_k1 k1 * Row_k1  +  sum_k0 k0 * Col_k0  +  sum_k B_k
+// with plain row and column sums (k_red_rowcol: every bucket is added twice, like the running sums do, but as short
+// serial pieces plus a tree inside the block), and the two small weighted sums are taken bit by bit,
+//     sum_j j * X_j = sum_b 2^b * T_b,   T_b = sum of the X_j whose index has bit b set      (k_red_bits: trees again),
+// so that what is left is ONE Horner chain over the c-1 bit positions per window (k_tail_group_bits: c-2 doublings and
+// c-1 additions, all windows of the group at once on their own teams), then the ordinary Horner over the windows.
+// Three launches, ~(8 + 8) + (c - 1) dependent additions instead of ~65.  All additions are 4-lane team additions.
+template <class P>
+ZK_D Xyzz<P> red_block_tree(const Team& tm, Xyzz<P> acc, int p, int tpo, XyzzMem<P>* sm) {
+  const int tq = threadIdx.x >> 2;
+  for (int s = 1; s < tpo; s <<= 1) {          // tpo is uniform over the block
+    if ((p & (2 * s - 1)) == s && tm.t == 0) store_xyzz<P>(&sm[tq], acc);
+    __syncthreads();
+    if ((p & (2 * s - 1)) == 0) xyzz_add_tm<P>(tm, acc, load_xyzz<P>(&sm[tq + s]));
+    __syncthreads();
+  }
+  return acc;
+}
+// blocks [0, row_blocks): row sums, the rest: column sums; blockIdx.y = window of the group.
+// RC[window][0 .. NR) = rows, RC[window][NR .. NR + NC) = columns.
+template <class C>
+__global__ void __launch_bounds__(128)
+k_red_rowcol(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices, size_t slice_stride, int hr, int hc,
+             int tpo_r, int tpo_c, unsigned row_blocks, XyzzMem<typename C::Fp>* __restrict__ RC) {
+  using P = typename C::Fp;
+  __shared__ XyzzMem<P> sm[32];
+  const Team tm;
+  const int tq = threadIdx.x >> 2;
+  const uint32_t NR = 1u << hr, NC = 1u << hc;
+  const bool rows = blockIdx.x < row_blocks;
+  const int tpo = rows ? tpo_r : tpo_c;
+  const uint32_t o = (rows ? blockIdx.x : blockIdx.x - row_blocks) * (32 / tpo) + tq / tpo;   // output of this team
+  const int p = tq % tpo;
+  const uint32_t cnt = rows ? NC : NR;
+  const bool valid = o < (rows ? NR : NC);        // a block may have more teams than there are sums (tiny windows)
+  const XyzzMem<P>* b = buckets + (size_t)blockIdx.y * ((size_t)NR * NC) + (rows ? (size_t)o * NC : (size_t)o);
+  const size_t stride = rows ? 1 : NC;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (uint32_t i = p; valid && i < cnt; i += tpo) {
+#pragma unroll 1
+    for (int k = 0; k < nslices; k++) xyzz_add_tm<P>(tm, acc, load_xyzz<P>(b + (size_t)k * slice_stride + i * stride));
+  }
+  acc = red_block_tree<P>(tm, acc, p, tpo, sm);
+  if (valid && p == 0 && tm.t == 0) store_xyzz<P>(RC + (size_t)blockIdx.y * (NR + NC) + (rows ? o : NR + o), acc);
+}
+// blockIdx.x = j: bit j of the column index (j < hc), bit j - hc of the row index (j < hc + hr), or the sum of all rows
+// (j = hc + hr); blockIdx.y = window.  T[window][j].
+template <class C>
+__global__ void __launch_bounds__(128)
+k_red_bits(const XyzzMem<typename C::Fp>* __restrict__ RC, int hr, int hc, XyzzMem<typename C::Fp>* __restrict__ T) {
+  using P = typename C::Fp;
+  __shared__ XyzzMem<P> sm[32];
+  const Team tm;
+  const int tq = threadIdx.x >> 2;
+  const uint32_t NR = 1u << hr, NC = 1u << hc;
+  const int j = blockIdx.x;
+  const XyzzMem<P>* src = RC + (size_t)blockIdx.y * (NR + NC);
+  uint32_t cnt;
+  int bit = -1;
+  if (j < hc) { src += NR; cnt = NC >> 1; bit = j; }
+  else if (j < hc + hr) { cnt = NR >> 1; bit = j - hc; }
+  else cnt = NR;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (uint32_t e = tq; e < cnt; e += 32) {
+    const uint32_t idx = bit < 0 ? e : (((e >> bit) << (bit + 1)) | (1u << bit) | (e & ((1u << bit) - 1u)));
+    xyzz_add_tm<P>(tm, acc, load_xyzz<P>(src + idx));
+  }
+  acc = red_block_tree<P>(tm, acc, tq, 32, sm);
+  if (tq == 0 && tm.t == 0) store_xyzz<P>(T + (size_t)blockIdx.y * (hr + hc + 1) + j, acc);
+}
+// One block, NCH teams per window of the group.  The window sum  sum_b 2^b T_b + T_all  is a Horner chain over the bit
+// positions; NCH teams take NCH contiguous pieces of it at the same time (piece q covers bits [lo_q, hi_q), its value is
+// sum_{b in piece} 2^(b - lo_q) T_b), then the window's first team joins the pieces top down (hi_q - lo_q doublings and
+// one addition each) -- the chain is (c-1)/NCH + NCH - 1 additions deep instead of c - 1.  Then team 0 of the block:
+// Horner over the windows (top first) and `extra` more doublings, as k_tail_group.
+template <class C, int NCH>
+__global__ void k_tail_group_bits(const XyzzMem<typename C::Fp>* __restrict__ T, int Wg, int c, int extra,
+                                  XyzzMem<typename C::Fp>* __restrict__ out) {
+  using P = typename C::Fp;
+  __shared__ XyzzMem<P> Rw[32];                   // piece values, then (slot w * NCH) the window sums
+  const Team tm;
+  const int tq = threadIdx.x >> 2, w = tq / NCH, q = tq % NCH;
+  const int nb = c - 1;                           // bit positions 0 .. nb-1
+  const int lo = (nb * q) / NCH, hi = (nb * (q + 1)) / NCH;
+  const XyzzMem<P>* t = T + (size_t)w * c;        // c - 1 bit sums and the plain sum
+  if (w < Wg) {                                   // whole teams take the branch
+    Xyzz<P> acc = xyzz_inf<P>();
+#pragma unroll 1
+    for (int b = hi - 1; b >= lo; b--) {
+      acc = xyzz_dbl_team<P>(tm, acc);            // no-op while acc is infinity
+      xyzz_add_tm<P>(tm, acc, load_xyzz<P>(t + b));
+    }
+    if (q == 0) xyzz_add_tm<P>(tm, acc, load_xyzz<P>(t + (c - 1)));
+    if (NCH > 1 && tm.t == 0) store_xyzz<P>(&Rw[tq], acc);
+    if (NCH > 1) __syncwarp(0xFFFFFFFFu >> (32 - 4 * NCH) << (4 * (tq - q) & 31));   // the window's teams share a warp
+    if (q == 0) {
+      if (NCH > 1) {
+        acc = load_xyzz<P>(&Rw[tq + NCH - 1]);
+#pragma unroll 1
+        for (int r = NCH - 2; r >= 0; r--) {
+          const int sh = (nb * (r + 1)) / NCH - (nb * r) / NCH;   // width of piece r: what is above it moves up by that much
+#pragma unroll 1
+          for (int d = 0; d < sh; d++) acc = xyzz_dbl_team<P>(tm, acc);
+          xyzz_add_tm<P>(tm, acc, load_xyzz<P>(&Rw[tq + r]));
+        }
+      }
+      __syncwarp(tm.mask);
+      if (tm.t == 0) store_xyzz<P>(&Rw[tq], acc);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= 4) return;
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int v = Wg - 1; v >= 0; v--) {
+    const int nd = v == Wg - 1 ? 0 : c;
+#pragma unroll 1
+    for (int d = 0; d < nd; d++) acc = xyzz_dbl_team<P>(tm, acc);
+    xyzz_add_tm<P>(tm, acc, load_xyzz<P>(&Rw[v * NCH]));
+  }
+#pragma unroll 1
+  for (int d = 0; d < extra; d++) acc = xyzz_dbl_team<P>(tm, acc);
+  if (tm.t == 0) store_xyzz<P>(out, acc);
+}
+// buckets of `ns` consecutive windows -> the group's share of the result (XYZZ) in *out.
+// Workspaces: RC ns * (2^hr + 2^hc) records, T ns * c records.
+template <class C>
+int launch_reduce_2d(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, int nslices, size_t slice_stride, int ns, int c, int extra,
+                     XyzzMem<typename C::Fp>* RC, XyzzMem<typename C::Fp>* T, XyzzMem<typename C::Fp>* out) {
+  const int hc = c / 2, hr = c - 1 - hc;          // hc >= hr
+  auto tpo_of = [](uint32_t cnt) { uint32_t t = cnt / 8; return (int)(t < 1 ? 1 : (t > 32 ? 32 : t)); };
+  const int tpo_r = tpo_of(1u << hc), tpo_c = tpo_of(1u << hr);
+  const unsigned row_blocks = (unsigned)((((size_t)1 << hr) * tpo_r + 31) / 32), col_blocks = (unsigned)((((size_t)1 << hc) * tpo_c + 31) / 32);
+  k_red_rowcol<C><<<dim3(row_blocks + col_blocks, ns), 128, 0, s>>>(buckets, nslices, slice_stride, hr, hc, tpo_r, tpo_c, row_blocks, RC);
+  k_red_bits<C><<<dim3(c, ns), 128, 0, s>>>(RC, hr, hc, T);
+  // pieces per window: as many as fit into one block of 32 teams (a window's teams must share a warp: 8 teams)
+  if (ns <= 8) k_tail_group_bits<C, 4><<<1, ((16 * ns + 31) / 32) * 32, 0, s>>>(T, ns, c, extra, out);
+  else if (ns <= 16) k_tail_group_bits<C, 2><<<1, ((8 * ns + 31) / 32) * 32, 0, s>>>(T, ns, c, extra, out);
+  else k_tail_group_bits<C, 1><<<1, ((4 * ns + 31) / 32) * 32, 0, s>>>(T, ns, c, extra, out);
+  return 3;
+}
+
 // ---- K6 + K7: window combination (Horner) and output conversion ------------------------------------------
 
 template <class P>
@@ -419,6 +564,8 @@ void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, i
   template void launch_tail<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, int, uint32_t*);                        \
   template void launch_sum_points<C>(cudaStream_t, const uint32_t*, int, int, int, uint32_t*);                             \
   template void launch_tail_group<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, int, int, XyzzMem<C::Fp>*);                 \
+  template int launch_reduce_2d<C>(cudaStream_t, const XyzzMem<C::Fp>*, int, size_t, int, int, int, XyzzMem<C::Fp>*,       \
+                                   XyzzMem<C::Fp>*, XyzzMem<C::Fp>*);                                                      \
   template void launch_gen_chain<C>(cudaStream_t, const uint32_t*, unsigned long long, size_t, uint32_t*);               \
   template void launch_batch_to_affine<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*, int);                         \
   template void launch_convert_z<C>(cudaStream_t, const uint32_t*, size_t, uint32_t*);                                     \

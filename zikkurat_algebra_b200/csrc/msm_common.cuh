@@ -100,14 +100,15 @@ constexpr int AFF_THREADS = 128;
 constexpr int BINV_G = 4;         // elements per thread in the product trees of the batch inversion
 struct AffWork {          // device workspaces, sized by aff_sizes()
   uint32_t* tmp;          // temporary affine points
-  uint32_t* pre;          // running products, one per merge of the widest level
+  uint32_t* pre;          // running products, one per merge of the widest level (levels 0, 2, ..)
+  uint32_t* pre2;         // the same for the odd levels (half the size)
   uint32_t* binv;         // thread totals + batch_invert workspace
   uint4* st[2];           // block states, ping-pong
   uint32_t* keys_out;     // records for k_accumulate: 2 * ceil(n / 2^R) per segment
   uint32_t* vals_out;
 };
 struct AffSizes {
-  size_t tmp_points, pre_elems, binv_elems, st0, st1, rec;
+  size_t tmp_points, pre_elems, pre2_elems, binv_elems, st0, st1, rec;
   uint32_t nrec;          // records per segment after the last level
 };
 // Levels of the batch inversion's product tree: big levels are thread-serial (BINV_GS elements per thread, no
@@ -143,7 +144,7 @@ inline AffSizes aff_sizes(size_t n, int nseg, int R) {
       z.binv_elems = blocks * AFF_THREADS + binv_workspace_elems(blocks * AFF_THREADS) + 64;
       z.st0 = (size_t)nseg * nm;
     }
-    if (r == 1) z.st1 = (size_t)nseg * nm;
+    if (r == 1) { z.st1 = (size_t)nseg * nm; z.pre2_elems = (size_t)nseg * nm; }
     nin = nm;
   }
   z.nrec = (uint32_t)(2 * nin);
@@ -183,6 +184,11 @@ template <class C> void launch_reduce_next(cudaStream_t s, const XyzzMem<typenam
 template <class C> void launch_tail(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int nmsm, int W, int c, int mode, uint32_t* out);
 template <class C> void launch_tail_group(cudaStream_t s, const XyzzMem<typename C::Fp>* Rw, int Wg, int c, int extra,
                                           XyzzMem<typename C::Fp>* out);
+constexpr int RED2D_MIN_BITS = 6;       // the low-latency reduction needs c - 1 >= this ...
+constexpr int RED2D_MAX_WINDOWS = 32;   // ... and at most this many windows per group (teams of k_tail_group_bits)
+// low-latency bucket reduction of `ns` consecutive windows (kernels_red.cuh): returns the number of launches
+template <class C> int launch_reduce_2d(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, int nslices, size_t slice_stride, int ns, int c,
+                                        int extra, XyzzMem<typename C::Fp>* RC, XyzzMem<typename C::Fp>* T, XyzzMem<typename C::Fp>* out);
 template <class C> void launch_sum_points(cudaStream_t s, const uint32_t* in, int k, int in_mode, int out_mode, uint32_t* out);
 template <class C> void launch_batch_to_affine(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* dst, int jac);
 template <class C> void launch_convert_z(cudaStream_t s, const uint32_t* src, size_t n, uint32_t* z_out);

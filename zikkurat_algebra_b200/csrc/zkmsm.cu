@@ -41,7 +41,7 @@ namespace {
 enum Buf {
   B_SCALARS, B_POINTS, B_KEYS0, B_KEYS1, B_VALS0, B_VALS1, B_CNT, B_ROWSUM, B_BUCKETS, B_HEADS, B_HEADKEYS, B_HEADS2, B_HEADKEYS2,
   B_U0, B_V0, B_U1, B_V1, B_OUT, B_NTT_TABLE, B_AFF_TMP, B_AFF_PRE, B_AFF_BINV, B_AFF_ST0, B_AFF_ST1, B_AFF_KEYS,
-  B_AFF_VALS, B_PARTIALS, B_GLV_POINTS, B_COUNT
+  B_AFF_VALS, B_PARTIALS, B_GLV_POINTS, B_RED_RC, B_RED_T, B_COUNT
 };
 constexpr int N_EV = 9;
 constexpr int MAX_DEV = 16;
@@ -624,7 +624,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       if (pairs_max >= ((size_t)1 << 30) || n * F >= ((size_t)1 << 30)) R = 0;   // 30-bit refs
       if (R > 0) {   // workspace guard: temporary points + running products
         AffSizes z = aff_sizes(pmax, nseg, R);
-        if ((z.tmp_points * OS + z.pre_elems * L) * (size_t)4 > ((size_t)48 << 30)) R = 0;
+        if ((z.tmp_points * OS + (z.pre_elems + z.pre2_elems) * L) * (size_t)4 > ((size_t)48 << 30)) R = 0;
       }
     }
     st.aff_levels = R;
@@ -722,7 +722,8 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       az = aff_sizes(pmax, nseg, R);
       binv_stride = az.binv_elems + 64;
       aw.tmp = (uint32_t*)cx.ensure(B_AFF_TMP, az.tmp_points * (size_t)OS * 4);
-      aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, az.pre_elems * (size_t)L * 4);
+      aw.pre = (uint32_t*)cx.ensure(B_AFF_PRE, (az.pre_elems + az.pre2_elems) * (size_t)L * 4);
+      aw.pre2 = aw.pre + az.pre_elems * (size_t)L;
       aw.binv = (uint32_t*)cx.ensure(B_AFF_BINV, 4 * binv_stride * (size_t)L * 4);
       aw.st[0] = (uint4*)cx.ensure(B_AFF_ST0, az.st0 * 16 + 16);
       aw.st[1] = (uint4*)cx.ensure(B_AFF_ST1, az.st1 * 16 + 16);
@@ -757,6 +758,15 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     Mem* Ub[2] = {(Mem*)cx.ensure(B_U0, red_out * sizeof(Mem)), (Mem*)cx.ensure(B_U1, red_out * sizeof(Mem))};
     Mem* Vb[2] = {(Mem*)cx.ensure(B_V0, red_out * sizeof(Mem)), (Mem*)cx.ensure(B_V1, red_out * sizeof(Mem))};
     Mem* partials = (Mem*)cx.ensure(B_PARTIALS, 16 * sizeof(Mem));
+    // low-latency reduction of the window groups (kernels_red.cuh, K5'): row / column sums and bit sums per window
+    const bool red2d_on = [] { const char* e = getenv("ZKB200_RED2D"); return e ? atoi(e) != 0 : true; }();   // per call: the tests switch it
+    const bool red2d = split_tail && red2d_on && c - 1 >= RED2D_MIN_BITS;
+    Mem* red_rc = nullptr;
+    Mem* red_t = nullptr;
+    if (red2d) {
+      red_rc = (Mem*)cx.ensure(B_RED_RC, (size_t)nseg * (((size_t)1 << (c - 1 - c / 2)) + ((size_t)1 << (c / 2))) * sizeof(Mem));
+      red_t = (Mem*)cx.ensure(B_RED_T, (size_t)nseg * c * sizeof(Mem));
+    }
     if (nlanes == 1) { cx.pl.big[0] = s; cx.pl.chain[0] = s; } else { cx.pl.big[0] = cx.pl.s_big[0]; cx.pl.chain[0] = cx.pl.s_chain[0]; }
     cx.pl.big[1] = cx.pl.s_big[1];
     cx.pl.chain[1] = cx.pl.s_chain[1];
@@ -882,28 +892,35 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
             cudaStream_t sp = cx.pl.post[gl[l]];
             CK(cudaEventRecord(cx.pl.ev_fix[gl[l]], sl));
             CK(cudaStreamWaitEvent(sp, cx.pl.ev_fix[gl[l]], 0));
-            const size_t ubase = (size_t)s0 << (c - 1 - log_mmin);
-            const bool team = gl[l] == 0 && reduce_team;   // the bottom group is the one the caller ends up waiting for
-            const int lm1 = team ? log_mt : log_m1;
-            int logS = c - 1;
-            size_t total_out = (size_t)ns << (logS - lm1);
-            g_launches++;
-            launch_reduce_first<C>(sp, buckets + (size_t)s0 * NB, K, slice_stride, total_out, lm1, Ub[0] + ubase, Vb[0] + ubase, team);
-            CK(cudaGetLastError());
-            logS -= lm1;
-            int lv = 0;
-            while (logS > 0) {
-              int lm = logS > 3 ? 3 : logS;
-              total_out = (size_t)ns << (logS - lm);
-              g_launches++;
-              launch_reduce_next<C>(sp, Ub[lv] + ubase, Vb[lv] + ubase, total_out, lm, Ub[lv ^ 1] + ubase, Vb[lv ^ 1] + ubase);
+            if (red2d && ns <= RED2D_MAX_WINDOWS) {
+              const size_t rc_per = ((size_t)1 << (c - 1 - c / 2)) + ((size_t)1 << (c / 2));
+              g_launches += launch_reduce_2d<C>(sp, buckets + (size_t)s0 * NB, K, slice_stride, ns, c, c * s0, red_rc + (size_t)s0 * rc_per,
+                                                red_t + (size_t)s0 * c, partials + gl[l]);
               CK(cudaGetLastError());
-              logS -= lm;
-              lv ^= 1;
+            } else {
+              const size_t ubase = (size_t)s0 << (c - 1 - log_mmin);
+              const bool team = gl[l] == 0 && reduce_team;   // the bottom group is the one the caller ends up waiting for
+              const int lm1 = team ? log_mt : log_m1;
+              int logS = c - 1;
+              size_t total_out = (size_t)ns << (logS - lm1);
+              g_launches++;
+              launch_reduce_first<C>(sp, buckets + (size_t)s0 * NB, K, slice_stride, total_out, lm1, Ub[0] + ubase, Vb[0] + ubase, team);
+              CK(cudaGetLastError());
+              logS -= lm1;
+              int lv = 0;
+              while (logS > 0) {
+                int lm = logS > 3 ? 3 : logS;
+                total_out = (size_t)ns << (logS - lm);
+                g_launches++;
+                launch_reduce_next<C>(sp, Ub[lv] + ubase, Vb[lv] + ubase, total_out, lm, Ub[lv ^ 1] + ubase, Vb[lv ^ 1] + ubase);
+                CK(cudaGetLastError());
+                logS -= lm;
+                lv ^= 1;
+              }
+              g_launches++;
+              launch_tail_group<C>(sp, Ub[lv] + ubase, ns, c, c * s0, partials + gl[l]);
+              CK(cudaGetLastError());
             }
-            g_launches++;
-            launch_tail_group<C>(sp, Ub[lv] + ubase, ns, c, c * s0, partials + gl[l]);
-            CK(cudaGetLastError());
             CK(cudaEventRecord(cx.pl.ev_post[gl[l]], sp));
           }
         }
