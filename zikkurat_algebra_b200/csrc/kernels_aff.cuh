@@ -188,8 +188,15 @@ k_aff_prefix(uint32_t total, uint32_t* __restrict__ pre, uint32_t* __restrict__ 
 // k_accumulate.  Slot layout [buffer][16-byte word][thread]: conflict-free.
 // Build-time experiment switches (tools/build_variant.py): resident blocks per SM asked of ptxas for k_aff_add, and
 // whether the stored running product travels through the shared-memory slot too (it costs a fifth of the slot).
-#ifndef ZK_AFF_MINB
-#define ZK_AFF_MINB 1
+// (No default for ZK_AFF_MINB: naming a minimum -- even 1 -- changes ptxas' register allocation; with "1" the 12-limb
+// kernels went from 158 to 172 registers, i.e. from three resident blocks to two, and levels 1-2 ran 11 % slower.)
+// 12-limb fields: three resident blocks are what the shared-memory slots allow, and the kernels sit right at the
+// register count that still permits them (164-172 without a bound, 170 is the limit), so the bound is stated there;
+// 0 = unspecified for the other fields.
+#ifdef ZK_AFF_MINB
+#define ZK_AFF_BOUNDS __launch_bounds__(AFF_THREADS, ZK_AFF_MINB)
+#else
+#define ZK_AFF_BOUNDS __launch_bounds__(AFF_THREADS, (C::Fp::L == 12 ? 3 : 0))
 #endif
 #ifndef ZK_AFF_STAGE_PRE
 #define ZK_AFF_STAGE_PRE 1
@@ -204,7 +211,7 @@ constexpr size_t aff_stage_bytes() { return (size_t)2 * aff_stage_words<P>() * A
 // NEXT: also hand the next level its denominators (dnext[m / 2], see the header); needs an even number of merges per
 // segment so that the two blocks of a next-level merge sit in neighbouring lanes.
 template <class C, bool LEVEL0, bool LAST, bool CALLS, bool NEXT>
-__global__ void __launch_bounds__(AFF_THREADS, ZK_AFF_MINB)
+__global__ void ZK_AFF_BOUNDS
 k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint4* __restrict__ st_in, uint32_t nin,
           uint32_t nm, uint32_t total, const uint32_t* points, int pstride, uint32_t* tmp, uint32_t tmp_off, const uint32_t* __restrict__ pre,
           const uint32_t* __restrict__ totinv, uint4* __restrict__ st_out, uint32_t* __restrict__ keys_out,
@@ -217,14 +224,21 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
   extern __shared__ uint4 aff_stage[];   // [2][NW][AFF_THREADS]
   const uint32_t tile = blockIdx.x * (uint32_t)(AFF_THREADS * B);
   Fe<P> r = ld_fe<P>(totinv + ((size_t)blockIdx.x * AFF_THREADS + threadIdx.x) * P::L);
-  // fetch(j): read the two blocks of merge j and start the copies of its operands
-  auto fetch = [&](int j, int buf, AffPair& a, uint32_t& seg, uint32_t& i) -> bool {
+  // Two steps ahead of the arithmetic: read_pair(j) loads the two blocks of merge j (eight words from global memory),
+  // one step ahead: issue(j) starts the copies of its operands -- the addresses come out of those words, so doing both
+  // in one step made every warp wait for the loads once per merge (ncu: 6 % of all stall samples on the one ISETP that
+  // first touches them).
+  auto read_pair = [&](int j, AffPair& a, uint32_t& seg, uint32_t& i) -> bool {
     const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
     if (j < 0 || m >= total) return false;
     seg = m / nm;
     i = m - seg * nm;
     a = aff_read_pair<LEVEL0>(keys, vals, st_in, nin, seg, i);
+    return true;
+  };
+  auto issue = [&](int j, int buf, const AffPair& a) {
     if (a.Ltk == a.Rhk && a.Ltk != 0) {
+      const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
       const uint4* s1 = reinterpret_cast<const uint4*>(aff_addr<P>(points, pstride, tmp, a.Ltr));
       const uint4* s2 = reinterpret_cast<const uint4*>(aff_addr<P>(points, pstride, tmp, a.Rhr));
       const uint4* s3 = reinterpret_cast<const uint4*>(pre + (size_t)m * P::L);
@@ -236,7 +250,6 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
       }
     }
-    return true;
   };
   auto staged = [&](int buf, int w0, uint32_t* out, int nwords) {
     const uint4* src = aff_stage + (size_t)buf * NW * AFF_THREADS + threadIdx.x;
@@ -246,13 +259,16 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
       out[4 * w] = q.x; out[4 * w + 1] = q.y; out[4 * w + 2] = q.z; out[4 * w + 3] = q.w;
     }
   };
-  AffPair a, an;
-  uint32_t seg = 0, i = 0, segn = 0, in_ = 0;
-  bool have = fetch(B - 1, (B - 1) & 1, a, seg, i);
+  AffPair a, an, ann;
+  uint32_t seg = 0, i = 0, segn = 0, in_ = 0, segnn = 0, inn = 0;
+  bool have = read_pair(B - 1, a, seg, i);
+  bool have_next = read_pair(B - 2, an, segn, in_);
+  if (have) issue(B - 1, (B - 1) & 1, a);
   asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll 1
   for (int j = B - 1; j >= 0; j--) {
-    const bool have_next = fetch(j - 1, (j - 1) & 1, an, segn, in_);
+    const bool have_nn = read_pair(j - 2, ann, segnn, inn);
+    if (have_next) issue(j - 1, (j - 1) & 1, an);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     const uint32_t m = tile + (uint32_t)j * AFF_THREADS + threadIdx.x;
@@ -356,6 +372,7 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
       if (!odd && have) st_fe<P>(dnext + (size_t)(m >> 1) * P::L, dn);
     }
     have = have_next; a = an; seg = segn; i = in_;
+    have_next = have_nn; an = ann; segn = segnn; in_ = inn;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }

@@ -150,10 +150,15 @@ k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typ
 // so that what is left is ONE Horner chain over the c-1 bit positions per window (k_tail_group_bits: c-2 doublings and
 // c-1 additions, all windows of the group at once on their own teams), then the ordinary Horner over the windows.
 // Three launches, ~(8 + 8) + (c - 1) dependent additions instead of ~65.  All additions are 4-lane team additions.
+// Sum of the partial values of each group of `tpo` consecutive teams of the block (tpo a power of two, uniform over the
+// block); the result is valid in the group's first team.  (Compacting the surviving teams into the first warps on every
+// level -- so that whole warps drop out -- was measured and lost: 185 -> 213 us for k_red_rowcol on two BLS12-381 windows;
+// the kernel is bound by the latency of its 13 dependent additions and the extra shared-memory round trip per level
+// costs more than the idle teams' pipe time.)
 template <class P>
 ZK_D Xyzz<P> red_block_tree(const Team& tm, Xyzz<P> acc, int p, int tpo, XyzzMem<P>* sm) {
   const int tq = threadIdx.x >> 2;
-  for (int s = 1; s < tpo; s <<= 1) {          // tpo is uniform over the block
+  for (int s = 1; s < tpo; s <<= 1) {
     if ((p & (2 * s - 1)) == s && tm.t == 0) store_xyzz<P>(&sm[tq], acc);
     __syncthreads();
     if ((p & (2 * s - 1)) == 0) xyzz_add_tm<P>(tm, acc, load_xyzz<P>(&sm[tq + s]));

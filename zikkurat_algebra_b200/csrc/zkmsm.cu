@@ -663,10 +663,13 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     }
     if (stagger) {
       nlanes = 1;
-      // priority level of every lane (lane 0 = top group), one digit each; default: top group above the rest, the
-      // others equal so that they hide each other's inversion chains
+      // priority level of every lane (lane 0 = top group), one digit each; default: the upper two groups above the
+      // bottom one, whose kernels then fill the holes the others' inversion chains leave and which finishes last -- it has
+      // the shortest post-processing chain (no trailing doublings).  Measured at BLS12-381 2^20, three runs each on one
+      // box: median call 6.81-6.84 ms with "1000", 6.61-6.65 with "1100", 6.70 with "2100"; best calls equal
+      // (6.5-6.6): "1000" lets the middle group end up alone on the GPU in half of the calls (profiles/r2_notes.md).
       const char* e = getenv("ZKB200_STAGGER_PRI");
-      const char* dflt = "1000";
+      const char* dflt = "1100";
       for (int j = 0; j < 4; j++) {
         int lv = (e && strlen(e) > (size_t)j ? e[j] : dflt[j]) - '0';
         if (lv < 0) lv = 0;
@@ -697,12 +700,15 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
     trace_groups = split_tail ? NG : 0;
     for (int g = 0; g <= NG; g++) trace_g0[g] = grp0[g];
     const int conc_segs = stagger ? nseg : (nseg + NG - 1) / NG * nlanes;   // segments in flight at a time
-    auto pick_chunk = [&](size_t per_seg) -> int {
+    // (records of the affine tree: half of the slots are empty and a lane's k_accumulate_rec runs next to the other
+    // lanes' kernels, so short chunks -- about 2.5 resident waves of threads over all lanes, at least 16 slots each --
+    // keep its latency down: BLS12-381 2^20 median call 6.53 -> 6.45 ms with 16 instead of 48 slots, 2^22 unchanged)
+    auto pick_chunk = [&](size_t per_seg, bool records = false) -> int {
       const char* e = getenv("ZKB200_CHUNK");
       if (e && atoi(e) > 0) return atoi(e);
       const size_t pairs_total = per_seg * (size_t)conc_segs;
-      double target = (double)pairs_total / ((double)resident * 12.0);
-      if (target < 48.0) target = 48.0;
+      double target = (double)pairs_total / ((double)resident * (records ? 2.5 : 12.0));
+      if (target < (records ? 16.0 : 48.0)) target = records ? 16.0 : 48.0;
       if (target > 192.0) target = 192.0;
       double waves = (double)pairs_total / ((double)resident * target);
       size_t nw = waves < 1.0 ? 1 : (size_t)(waves + 0.5);
@@ -729,7 +735,7 @@ void run_msm(DeviceCtx& cx, int nmsm, size_t n, const uint64_t* scalars, int slo
       aw.st[1] = (uint4*)cx.ensure(B_AFF_ST1, az.st1 * 16 + 16);
       aw.keys_out = (uint32_t*)cx.ensure(B_AFF_KEYS, az.rec * 4 + 16);
       aw.vals_out = (uint32_t*)cx.ensure(B_AFF_VALS, az.rec * 4 + 16);
-      chunk_rec = pick_chunk(az.nrec);
+      chunk_rec = pick_chunk(az.nrec, true);
     }
     uint32_t cps_max = (uint32_t)((pmax + chunk - 1) / chunk);
     if (R > 0) {
