@@ -735,7 +735,7 @@ int launch_affine_tree(const AffLanes& ln, const uint32_t* keys, const uint32_t*
   uint32_t* inv[2] = {nullptr, nullptr};
   // Running products of level r live in w.pre (even r) or w.pre2 (odd r): level r's additions read theirs while they
   // write the next level's denominators into the other array.
-  // Measured (profiles/r2_notes.md section 10): the prefix kernels save 0.13 ms of serialised kernel time per BLS12-381
+  // Measured (profiles/r2_notes.md section 9): the prefix kernels save 0.13 ms of serialised kernel time per BLS12-381
   // 2^20 MSM but the additions grow by 0.22 ms (shuffles, a second classification, a fetch for every operand that is not
   // the new sum), so the hand-over is opt-in ($ZKB200_AFF_NEXT=1; read per call so that the tests can switch it).
   const bool next_on = [] { const char* e = getenv("ZKB200_AFF_NEXT"); return e ? atoi(e) != 0 : false; }();
