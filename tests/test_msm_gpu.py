@@ -791,6 +791,14 @@ def test_reduction_and_handover_switches(zk, curve):
             with _Env(ZKB200_RED2D=red):
                 out = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_proj_out_variable", sc, pts, window_size=c)
             assert to_affine_cpu(curve, "proj", out).tobytes() == want, (red, c)
+        zk.set_glv(0)      # wide windows with enough of them for window groups: 255-bit scalars
+        try:
+            for c in (19, 21):
+                with _Env(ZKB200_RED2D=red):
+                    out = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_proj_out_variable", sc, pts, window_size=c)
+                assert to_affine_cpu(curve, "proj", out).tobytes() == want, (red, c, "no glv")
+        finally:
+            zk.set_glv(1)
         for K in (1, 3):   # input slices: several bucket arrays summed on the fly by the first reduction step
             with _Env(ZKB200_RED2D=red, ZKB200_SLICES=K):
                 got = zk.call_reference_symbol(f"{curve}_G1_proj_MSM_std_coeff_affine_out", sc, pts)
