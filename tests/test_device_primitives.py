@@ -107,6 +107,9 @@ def test_fp_ops_device_vs_reference(zk, curve):
     want_mul2 = cpu_map3(f"{curve}_Fp_mont_add", np.ascontiguousarray(want_mul[:m]), cpu_map3(f"{curve}_Fp_mont_mul", c2, d2, L), L)
     for op in ("mul2", "mul2_call"):
         assert np.array_equal(zk.selftest_field(curve, "Fp", op, a2, b2, c2, d2), want_mul2), op
+    # paired products a*b, a*c with their rows taken in turns (the peel-off step of the batched-affine additions)
+    assert np.array_equal(zk.selftest_field(curve, "Fp", "pair_first", a2, b2, c2), np.ascontiguousarray(want_mul[:m]))
+    assert np.array_equal(zk.selftest_field(curve, "Fp", "pair_second", a2, b2, c2), cpu_map3(f"{curve}_Fp_mont_mul", a2, c2, L))
     # inversion (Kaliski on the device, binary Euclid in the reference): same canonical value; 0 is skipped by both callers
     k = 20_000
     ai = a[:k].copy()

@@ -111,6 +111,29 @@ def test_fp_fused_mul_add(he, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_fp_paired_products(he, curve):
+    """mont_mul_pair_limbs (fp.cuh): a*b and a*c with their rows taken in turns must equal two plain products."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    rng = random.Random(33)
+    f = getattr(he, f"he_{curve}_fp_mul_pair")
+    f.argtypes = [refs.U64P] * 5
+    f.restype = None
+    Rinv = pow(cv.R, -1, cv.p)
+    edge = [0, 1, cv.p - 1, cv.p - 2, (1 << (64 * L - 3)) % cv.p, cv.R % cv.p, (1 << 32) - 1, (cv.p - 1) >> 1]
+    trip = [(a, b, c) for a in edge for b in edge for c in edge]
+    trip += [tuple(rng.randrange(cv.p) for _ in range(3)) for _ in range(3000)]
+    trip += [tuple(cv.p - 1 - rng.randrange(1 << 40) for _ in range(3)) for _ in range(500)]
+    trip += [tuple(rng.randrange(1 << 70) for _ in range(3)) for _ in range(300)]
+    for a, b, c in trip:
+        arrs = [_arr(x.to_bytes(8 * L, "little")) for x in (a, b, c)]
+        o1, o2 = np.zeros(L, np.uint64), np.zeros(L, np.uint64)
+        f(*[refs.ptr(x) for x in arrs], refs.ptr(o1), refs.ptr(o2))
+        assert int.from_bytes(o1.tobytes(), "little") == a * b * Rinv % cv.p
+        assert int.from_bytes(o2.tobytes(), "little") == a * c * Rinv % cv.p
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_fp_mul_matches_oracle_bytes(he, curve):
     L = refs.CURVE_LIMBS[curve]
     cv = pyec.CURVES[curve]

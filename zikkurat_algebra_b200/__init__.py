@@ -55,7 +55,7 @@ EXTENSION_SYMBOLS = ["zkb200_msm", "zkb200_sum_points", "zkb200_set_device", "zk
                      "zkb200_selftest_field", "zkb200_selftest_group", "zkb200_last_op_ms", "zkb200_set_glv"]
 FIELD_IDS = {("bn128", "Fp"): 0, ("bls12_381", "Fp"): 1, ("bn128", "Fr"): 2, ("bls12_381", "Fr"): 3}
 FIELD_OPS = {"mul": 0, "sqr": 1, "mul2": 2, "add": 3, "sub": 4, "neg": 5, "inv": 6, "mul_call": 7, "sqr_call": 8, "mul2_call": 9,
-             "dbl": 10, "from_mont": 11}
+             "dbl": 10, "from_mont": 11, "pair_first": 12, "pair_second": 13}
 GROUP_OPS = {"madd": 0, "madd_calls": 1, "add": 2, "add_calls": 3, "dbl": 4, "dbl_affine": 5}
 
 _U64P = ctypes.POINTER(ctypes.c_uint64)

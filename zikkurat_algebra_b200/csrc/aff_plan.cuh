@@ -56,6 +56,26 @@ ZK_HD Fe<P> aff_mul(const Fe<P>& a, const Fe<P>& b) {
   if constexpr (CALLS) return fe_mul_call<P>(a, b);
   else return fe_mul<P>(a, b);
 }
+// a*b and a*c at once (fp.cuh: mont_mul_pair_limbs) for prime fields with out-of-line multiplications; two plain products otherwise
+template <class P, class = void> struct AffIsExt { static constexpr bool value = false; };
+template <class P> struct AffIsExt<P, decltype((void)sizeof(typename P::Base))> { static constexpr bool value = true; };
+template <class P, bool CALLS>
+ZK_HD void aff_mul_pair(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, Fe<P>& ab, Fe<P>& ac) {
+#ifdef ZK_AFF_NO_PAIR   // build-time experiment switch (tools/build_variant.py)
+  constexpr bool PAIR = false;
+#else
+  constexpr bool PAIR = CALLS && !AffIsExt<P>::value;
+#endif
+  if constexpr (PAIR) {
+    FePair<P> r = fe_mul_pair_call<P>(a, b, c);
+    ab = r.u;
+    ac = r.v;
+  } else {
+    const Fe<P> a0 = a;
+    ab = aff_mul<P, CALLS>(a0, b);
+    ac = aff_mul<P, CALLS>(a0, c);
+  }
+}
 template <class P, bool CALLS>
 ZK_HD Fe<P> aff_sqr(const Fe<P>& a) {
   if constexpr (CALLS) return fe_sqr_call<P>(a);

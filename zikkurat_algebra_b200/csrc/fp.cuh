@@ -114,6 +114,67 @@ ZK_HD void mont_mul_limbs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   final_sub<P>(r);
 }
 
+// Two products with a common factor, r1 = a*b and r2 = a*c, row by row in turns: twice the independent carry chains in
+// flight (a single product gives the scheduler two to three, and a dependent IMAD.WIDE issues ~11 cycles after its
+// predecessor while the pipe could take one every 4).  Used where both products are needed anyway: the inverse peeled off a
+// batch inversion (r * prefix) and the running inverse itself (r * d) in the batched-affine additions.
+template <class P>
+ZK_HD void mont_mul_row0(uint32_t* A, uint32_t* B, const uint32_t* a, uint32_t b0) {
+  constexpr int L = P::L;
+#pragma unroll
+  for (int j = 0; j < L; j += 2) {
+    A[j] = mul_lo(a[j], b0);
+    A[j + 1] = mul_hi(a[j], b0);
+    B[j] = mul_lo(a[j + 1], b0);
+    B[j + 1] = mul_hi(a[j + 1], b0);
+  }
+  uint32_t m = mul_lo(A[0], P::INV);
+  cmad_row_const<L>(B, ModRow<P, 1>(), m);  // carry out is provably 0
+  cmad_row_const<L>(A, ModRow<P, 0>(), m);
+  B[L - 1] = addc(B[L - 1], 0u);
+}
+template <class P>
+ZK_HD void mont_mul_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {   // E: even accumulator of this row
+  constexpr int L = P::L;
+  E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 0; j < L - 2; j += 2) {
+    O[j] = madc_lo_cc(a[j + 1], bi, O[j + 2]);
+    O[j + 1] = madc_hi_cc(a[j + 1], bi, O[j + 3]);
+  }
+  O[L - 2] = madc_lo_cc(a[L - 1], bi, 0u);
+  O[L - 1] = madc_hi(a[L - 1], bi, 0u);
+  cmad_row<L, false>(E, a, bi);
+  O[L - 1] = addc(O[L - 1], 0u);
+  uint32_t m = mul_lo(E[0], P::INV);
+  cmad_row_const<L>(O, ModRow<P, 1>(), m);
+  cmad_row_const<L>(E, ModRow<P, 0>(), m);
+  O[L - 1] = addc(O[L - 1], 0u);
+}
+template <class P>
+ZK_HD void mont_mul_finish(uint32_t* r, const uint32_t* E, const uint32_t* O) {
+  constexpr int L = P::L;
+  r[0] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 1; k < L - 1; k++) r[k] = addc_cc(E[k + 1], O[k]);
+  r[L - 1] = addc(O[L - 1], 0u);
+  final_sub<P>(r);
+}
+template <class P>
+ZK_HD void mont_mul_pair_limbs(uint32_t* r1, uint32_t* r2, const uint32_t* a, const uint32_t* b, const uint32_t* c) {
+  constexpr int L = P::L;
+  uint32_t A1[L], B1[L], A2[L], B2[L];
+  mont_mul_row0<P>(A1, B1, a, b[0]);
+  mont_mul_row0<P>(A2, B2, a, c[0]);
+#pragma unroll
+  for (int i = 1; i < L; i++) {
+    mont_mul_row<P>((i & 1) ? B1 : A1, (i & 1) ? A1 : B1, a, b[i]);
+    mont_mul_row<P>((i & 1) ? B2 : A2, (i & 1) ? A2 : B2, a, c[i]);
+  }
+  mont_mul_finish<P>(r1, ((L - 1) & 1) ? B1 : A1, ((L - 1) & 1) ? A1 : B1);
+  mont_mul_finish<P>(r2, ((L - 1) & 1) ? B2 : A2, ((L - 1) & 1) ? A2 : B2);
+}
+
 // Fused r = (a*b + c*d) * R^-1 mod p with ONE interleaved reduction: 3L^2 + L products instead of the
 // 4L^2 + 2L of two separate multiplications (used for Y3 = R*(Q-X3) + (-Y1)*PPP in every group addition).
 // Inputs canonical.  Row bound: T_i < 3p(1 + 2^-32), and T + 3*2^32*p < 2^(32(L+1)) needs 3p < 2^(32L)
@@ -276,6 +337,14 @@ __device__ __noinline__ Fe<P> fe_sqr_call(Fe<P> a) {
   return fe_sqr<P>(a);
 }
 template <class P>
+struct FePair { Fe<P> u, v; };
+template <class P>
+__device__ __noinline__ FePair<P> fe_mul_pair_call(Fe<P> a, Fe<P> b, Fe<P> c) {
+  FePair<P> r;
+  mont_mul_pair_limbs<P>(r.u.l, r.v.l, a.l, b.l, c.l);
+  return r;
+}
+template <class P>
 __device__ __noinline__ Fe<P> fe_mul2_call(Fe<P> a, Fe<P> b, Fe<P> c, Fe<P> d) {
   Fe<P> r;
   mont_mul2_limbs<P>(r.l, a.l, b.l, c.l, d.l);
@@ -286,6 +355,14 @@ template <class P>
 inline Fe<P> fe_mul_call(Fe<P> a, Fe<P> b) { return fe_mul<P>(a, b); }
 template <class P>
 inline Fe<P> fe_sqr_call(Fe<P> a) { return fe_sqr<P>(a); }
+template <class P>
+struct FePair { Fe<P> u, v; };
+template <class P>
+inline FePair<P> fe_mul_pair_call(Fe<P> a, Fe<P> b, Fe<P> c) {
+  FePair<P> r;
+  mont_mul_pair_limbs<P>(r.u.l, r.v.l, a.l, b.l, c.l);
+  return r;
+}
 template <class P>
 inline Fe<P> fe_mul2_call(Fe<P> a, Fe<P> b, Fe<P> c, Fe<P> d) {
   Fe<P> r;

@@ -302,8 +302,8 @@ k_aff_add(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, 
           Fe<P> pr;
           if constexpr (SPRE) staged(j & 1, 2 * PW, pr.l, FW);
           else pr = ld_fe<P>(pre + (size_t)m * P::L);
-          Fe<P> dinv = aff_mul<P, CALLS>(r, pr);
-          r = aff_mul<P, CALLS>(r, d);
+          Fe<P> dinv;
+          aff_mul_pair<P, CALLS>(r, pr, d, dinv, r);   // 1/d of this merge, and the running inverse without it
           s = aff_finish<P, CALLS>(cls, p1, p2, dinv);
         } else if (cls == AFF_COPY2) {
           s = p2;

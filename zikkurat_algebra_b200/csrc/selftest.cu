@@ -55,6 +55,12 @@ __global__ void __launch_bounds__(128) k_selftest_field(int op, size_t n, const 
       break;
     case ZKT_DBL: r = fe_dbl<P>(x); break;
     case ZKT_FROM_MONT: r = fe_from_mont<P>(x); break;
+    case ZKT_PAIR_FIRST:
+    case ZKT_PAIR_SECOND: {
+      FePair<P> pr = fe_mul_pair_call<P>(x, y, st_ld<P>(c, i));
+      r = op == ZKT_PAIR_FIRST ? pr.u : pr.v;
+      break;
+    }
     default: r = fe_zero<P>(); break;
   }
   st_st<P>(out, i, r);

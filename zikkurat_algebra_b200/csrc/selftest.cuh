@@ -9,7 +9,8 @@ namespace zk {
 
 enum SelftestFieldOp : int {
   ZKT_MUL = 0, ZKT_SQR = 1, ZKT_MUL2 = 2, ZKT_ADD = 3, ZKT_SUB = 4, ZKT_NEG = 5, ZKT_INV = 6,
-  ZKT_MUL_CALL = 7, ZKT_SQR_CALL = 8, ZKT_MUL2_CALL = 9, ZKT_DBL = 10, ZKT_FROM_MONT = 11
+  ZKT_MUL_CALL = 7, ZKT_SQR_CALL = 8, ZKT_MUL2_CALL = 9, ZKT_DBL = 10, ZKT_FROM_MONT = 11,
+  ZKT_PAIR_FIRST = 12, ZKT_PAIR_SECOND = 13   // a*b resp. a*c out of the paired product fe_mul_pair_call(a, b, c)
 };
 enum SelftestGroupOp : int {
   ZKT_G_MADD = 0, ZKT_G_MADD_CALLS = 1, ZKT_G_ADD = 2, ZKT_G_ADD_CALLS = 3, ZKT_G_DBL = 4, ZKT_G_DBL_AFFINE = 5
