@@ -147,9 +147,12 @@ k_reduce_next(const XyzzMem<typename C::Fp>* __restrict__ Uin, const XyzzMem<typ
 // with plain row and column sums (k_red_rowcol: every bucket is added twice, like the running sums do, but as short
 // serial pieces plus a tree inside the block), and the two small weighted sums are taken bit by bit,
 //     sum_j j * X_j = sum_b 2^b * T_b,   T_b = sum of the X_j whose index has bit b set      (k_red_bits: trees again),
-// so that what is left is ONE Horner chain over the c-1 bit positions per window (k_tail_group_bits: c-2 doublings and
-// c-1 additions, all windows of the group at once on their own teams), then the ordinary Horner over the windows.
-// Three launches, ~(8 + 8) + (c - 1) dependent additions instead of ~65.  All additions are 4-lane team additions.
+// so that what is left is ONE Horner chain over the c-1 bit positions per window (k_tail_group_bits: cut into pieces that
+// several teams evaluate at the same time, all windows of the group at once), then the ordinary Horner over the windows.
+// Three launches and about 13 + 9 + (c-1)/4 + 3 dependent additions (c = 16: 29) instead of ~65; measured under ncu for two
+// BLS12-381 windows 185 + 63 + 184 us against 143 + 309 + 80 (profiles/r2_notes.md section 10).  All additions are 4-lane
+// team additions.
+
 // Sum of the partial values of each group of `tpo` consecutive teams of the block (tpo a power of two, uniform over the
 // block); the result is valid in the group's first team.  (Compacting the surviving teams into the first warps on every
 // level -- so that whole warps drop out -- was measured and lost: 185 -> 213 us for k_red_rowcol on two BLS12-381 windows;
