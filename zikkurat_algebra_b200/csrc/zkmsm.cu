@@ -281,7 +281,9 @@ struct StagePool {
   // multi-GPU arrangement, and 8 x 4 staging threads on a 32-core box fight each other) -- between 2 and 8
   // ($ZKB200_STAGE_THREADS overrides).  A slot is always reused by the same thread: chunk i uses slot i % (2T) and
   // belongs to thread i % T.
-  int T = 4;
+  int T = 4;        // threads of the pool
+  int Tjob = 4;     // threads working on the current job (small copies use at most 4, see copy())
+  bool forced = false;
   std::mutex m;
   std::condition_variable cv_work, cv_done;
   uint64_t gen = 0;
@@ -294,13 +296,15 @@ struct StagePool {
 
   explicit StagePool(DeviceCtx* c) : cx(c) {
     const char* e = getenv("ZKB200_STAGE_THREADS");
-    if (e && atoi(e) > 0) T = atoi(e);
+    if (e && atoi(e) > 0) { T = atoi(e); forced = true; }
     else {
       int gpus = 1;
       if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) gpus = 1;
       const unsigned hc = std::thread::hardware_concurrency();
       T = (int)(hc ? hc : 8) / gpus;
-      if (T > 4) T = 4;          // measured (B200 box, 16 cores, 32 MB of scalars): 2 threads 8.0 ms, 4: 7.7, 8: 8.3 per call
+      // measured (B200 box, 16 cores): 32 MB of scalars per call: 2 threads 8.0 ms, 4: 7.7, 8: 8.3; 128 MB (scalars and
+      // points of BLS12-381 2^20, no resident copy): 2: 11.1 ms, 4: 9.5, 8: 9.1, 12: 9.1; 384 MB (BN254 2^22): 4: 26.4, 8: 17.9
+      if (T > 8) T = 8;
     }
     if (T < 2) T = 2;
     if (T > DeviceCtx::STAGE_SLOTS / 2) T = DeviceCtx::STAGE_SLOTS / 2;
@@ -310,15 +314,18 @@ struct StagePool {
     if (cudaSetDevice(cx->dev) != cudaSuccess) abort();
     uint64_t seen = 0;
     for (;;) {
+      int TJ;
       {
         std::unique_lock<std::mutex> lk(m);
         cv_work.wait(lk, [&] { return gen != seen; });
         seen = gen;
-      }
-      const int R = 2 * T;
+        TJ = Tjob;                                // the job this generation belongs to (a thread that is not part of a
+      }                                           // job is not waited for, so it must not look at the job any later)
+      if (w >= TJ) continue;
+      const int R = 2 * TJ;
       constexpr size_t CH = DeviceCtx::STAGE_BYTES;
       const size_t nchunks = (bytes + CH - 1) / CH;
-      for (size_t i = w; i < nchunks; i += T) {
+      for (size_t i = w; i < nchunks; i += TJ) {
         const int slot = (int)(i % R);
         if (cx->stage_used[slot]) CK(cudaEventSynchronize(cx->stage_ev[slot]));   // previous DMA out of this slot finished
         const size_t off = i * CH, len = bytes - off < CH ? bytes - off : CH;
@@ -336,7 +343,8 @@ struct StagePool {
   void copy(uint8_t* d, const uint8_t* s, size_t n, cudaStream_t st) {   // returns when every chunk has been queued
     std::unique_lock<std::mutex> lk(m);
     dst = d; src = s; bytes = n; stream = st;
-    pending = T;
+    Tjob = (forced || n >= ((size_t)48 << 20) || T < 4) ? T : 4;   // more than 4 threads only pay for big copies
+    pending = Tjob;
     gen++;
     cv_work.notify_all();
     cv_done.wait(lk, [&] { return pending == 0; });
