@@ -529,6 +529,15 @@ def test_g2_msm_next_row(zk, curve):
             with _Env(ZKB200_AFFINE=R, **mode):
                 got = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_mont_coeff_affine_out", sc, pts, npoints=n)
             assert got.tobytes() == want.tobytes(), (n, R, mode)
+    # wide windows (the row / column bucket reduction of kernels_red.cuh takes over from c = 7) and its switch, over Fp2
+    n = 700
+    pts, sc = pts_all[:n], refs.random_scalars(curve, n, seed=4242, reduce=True)
+    want = refs.call_msm(lib, f"{curve}_G2_proj_MSM_mont_coeff_affine_out", sc.ravel(), pts.ravel(), W, n=n)
+    for c in (7, 10, 13):
+        for red in (0, 1):
+            with _Env(ZKB200_WINDOW=c, ZKB200_RED2D=red):
+                got = zk.call_reference_symbol(f"{curve}_G2_proj_MSM_mont_coeff_affine_out", sc, pts, npoints=n)
+            assert got.tobytes() == want.tobytes(), (c, red)
     # GPU chain generator for G2 == reference chain; larger size by the split property
     D = refs.call3(lib, f"{curve}_G2_affine_add", refs.call3(lib, f"{curve}_G2_affine_add", pts_all[0].copy(), pts_all[0].copy(), W), pts_all[0].copy(), W)
     assert zk.gen_chain(g2, 50, pts_all[0], D).tobytes() == pts_all[:50].tobytes()
