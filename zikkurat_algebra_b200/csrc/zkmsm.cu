@@ -257,7 +257,8 @@ bool host_is_pinned(const void* p) {
 // aligned (ring slots are multiples of 2 MiB inside a page-aligned allocation); src has the caller's alignment.
 #if defined(__x86_64__) && defined(__SSE2__)
 #include <emmintrin.h>
-inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n, bool streaming) {
+  if (!streaming) { memcpy(dst, src, n); return; }
   size_t i = 0;
   for (; i + 64 <= n; i += 64) {
     const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
@@ -271,7 +272,7 @@ inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) {
   _mm_sfence();      // the stores are globally visible before the DMA is queued
 }
 #else
-inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n) { memcpy(dst, src, n); }
+inline void stage_copy(uint8_t* dst, const uint8_t* src, size_t n, bool) { memcpy(dst, src, n); }
 #endif
 
 // Persistent staging threads (created on the first pageable copy of a device, never joined: they sleep on a condition
@@ -284,6 +285,8 @@ struct StagePool {
   int T = 4;        // threads of the pool
   int Tjob = 4;     // threads working on the current job (small copies use at most 4, see copy())
   bool forced = false;
+  size_t chunk = DeviceCtx::STAGE_BYTES;   // bytes per ring slot in use ($ZKB200_STAGE_CHUNK_KB, at most the slot size)
+  bool streaming = true;                   // non-temporal stores into the ring ($ZKB200_STAGE_NT=0: ordinary stores)
   std::mutex m;
   std::condition_variable cv_work, cv_done;
   uint64_t gen = 0;
@@ -308,6 +311,11 @@ struct StagePool {
     }
     if (T < 2) T = 2;
     if (T > DeviceCtx::STAGE_SLOTS / 2) T = DeviceCtx::STAGE_SLOTS / 2;
+    if (const char* q = getenv("ZKB200_STAGE_CHUNK_KB")) {
+      const size_t kb = (size_t)atoll(q);
+      if (kb >= 16 && (kb << 10) <= DeviceCtx::STAGE_BYTES) chunk = (kb << 10) & ~(size_t)63;
+    }
+    if (const char* q = getenv("ZKB200_STAGE_NT")) streaming = atoi(q) != 0;
     for (int w = 0; w < T; w++) std::thread([this, w] { worker(w); }).detach();
   }
   void worker(int w) {
@@ -323,14 +331,15 @@ struct StagePool {
       }                                           // job is not waited for, so it must not look at the job any later)
       if (w >= TJ) continue;
       const int R = 2 * TJ;
-      constexpr size_t CH = DeviceCtx::STAGE_BYTES;
+      const size_t CH = chunk;
       const size_t nchunks = (bytes + CH - 1) / CH;
       for (size_t i = w; i < nchunks; i += TJ) {
         const int slot = (int)(i % R);
         if (cx->stage_used[slot]) CK(cudaEventSynchronize(cx->stage_ev[slot]));   // previous DMA out of this slot finished
         const size_t off = i * CH, len = bytes - off < CH ? bytes - off : CH;
-        stage_copy(cx->stage + (size_t)slot * CH, src + off, len);
-        CK(cudaMemcpyAsync(dst + off, cx->stage + (size_t)slot * CH, len, cudaMemcpyHostToDevice, stream));
+        uint8_t* ring = cx->stage + (size_t)slot * DeviceCtx::STAGE_BYTES;
+        stage_copy(ring, src + off, len, streaming);
+        CK(cudaMemcpyAsync(dst + off, ring, len, cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(cx->stage_ev[slot], stream));
         cx->stage_used[slot] = true;
       }
