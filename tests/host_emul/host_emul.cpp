@@ -9,6 +9,7 @@
 #include "recode.cuh"
 #include "aff_plan.cuh"
 #include "glv.cuh"
+#include "red_plan.cuh"
 #include <vector>
 
 using namespace zk;
@@ -201,3 +202,54 @@ extern "C" void he_recode(const uint64_t* scalar, int nbits, int c, int nwin, ui
     st<C::Fp>(t, glv_beta_x<C::Fp, GlvOf<C>::type>(ld<C::Fp>(x))); }
 DEFINE_GLV(bn128, Bn254)
 DEFINE_GLV(bls12_381, Bls12381)
+
+// Model of the low-latency bucket reduction (kernels_red.cuh K5') over the integers mod m: the same three steps with the
+// same index functions (red_plan.cuh), group addition = addition mod m, doubling = times two.  buckets: 2^(c-1) values.
+extern "C" uint64_t he_red2d_model(int c, int nch, const uint64_t* buckets, uint64_t m) {
+  const RedPlan pl = red_plan(c);
+  const uint32_t NR = 1u << pl.hr, NC = 1u << pl.hc;
+  auto add = [&](uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a + b) % m); };
+  std::vector<uint64_t> RC(NR + NC, 0), seen(NR + NC, 0);
+  for (unsigned blk = 0; blk < pl.row_blocks + pl.col_blocks; blk++) {
+    uint64_t part[32];
+    RedTask tk[32];
+    for (int tq = 0; tq < 32; tq++) {
+      tk[tq] = red_rowcol_task(pl, blk, tq);
+      uint64_t acc = 0;
+      for (uint32_t i = tk[tq].part; tk[tq].valid && i < tk[tq].entries; i += tk[tq].tpo) acc = add(acc, buckets[tk[tq].first + (size_t)i * tk[tq].stride]);
+      part[tq] = acc;
+    }
+    for (int tq = 0; tq < 32; tq++) {          // red_block_tree: the group's first team ends up with the group's sum
+      if (tk[tq].part != 0 || !tk[tq].valid) continue;
+      uint64_t acc = 0;
+      for (int k = 0; k < tk[tq].tpo; k++) acc = add(acc, part[tq + k]);
+      const uint32_t slot = tk[tq].rows ? tk[tq].out : NR + tk[tq].out;
+      RC[slot] = acc;
+      seen[slot]++;
+    }
+  }
+  for (uint32_t i = 0; i < NR + NC; i++) if (seen[i] != 1) return ~(uint64_t)0;   // every sum written exactly once
+  std::vector<uint64_t> T(c, 0);
+  for (int j = 0; j < c; j++) {
+    const RedBits bt = red_bits_task(pl, j);
+    for (uint32_t e = 0; e < bt.entries; e++) T[j] = add(T[j], RC[bt.base + red_bit_member(e, bt.bit)]);
+  }
+  const int nb = c - 1;
+  std::vector<uint64_t> V(nch, 0);
+  for (int q = 0; q < nch; q++) {
+    int lo, hi;
+    red_piece(nb, nch, q, lo, hi);
+    uint64_t acc = 0;
+    for (int b = hi - 1; b >= lo; b--) acc = add(add(acc, acc), T[b]);
+    if (q == 0) acc = add(acc, T[c - 1]);
+    V[q] = acc;
+  }
+  uint64_t acc = V[nch - 1];
+  for (int r = nch - 2; r >= 0; r--) {
+    int lo, hi;
+    red_piece(nb, nch, r, lo, hi);
+    for (int d = 0; d < hi - lo; d++) acc = add(acc, acc);
+    acc = add(acc, V[r]);
+  }
+  return acc;
+}

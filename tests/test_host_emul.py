@@ -361,3 +361,22 @@ def test_glv_split_and_endomorphism(he, curve):
         X = _arr(cv.fp_to_bytes(P[0]))
         got = cv.fp_from_bytes(refs.call2(he, f"he_{curve}_glv_beta_x", X, L).tobytes())
         assert (got, P[1]) == cv.mul(lam, P)
+
+
+def test_low_latency_bucket_reduction_index_logic(he):
+    """red_plan.cuh: the row / column sums, the bit sums and the Horner chain cut into pieces (kernels_red.cuh K5') give
+    sum_k (k + 1) B_k for every window width the path accepts and every piece count -- checked over the integers mod a
+    prime with the same index functions the kernels use."""
+    f = he.he_red2d_model
+    f.argtypes = [ctypes.c_int, ctypes.c_int, refs.U64P, ctypes.c_uint64]
+    f.restype = ctypes.c_uint64
+    m = (1 << 61) - 1
+    rng = np.random.Generator(np.random.PCG64(77))
+    for c in range(7, 19):
+        nb = 1 << (c - 1)
+        b = rng.integers(0, m, size=nb, dtype=np.uint64)
+        if c % 3 == 0:
+            b[rng.integers(0, nb, size=nb // 2)] = 0          # empty buckets
+        want = sum((k + 1) * int(v) for k, v in enumerate(b)) % m
+        for nch in (1, 2, 4):
+            assert int(f(c, nch, refs.ptr(b), m)) == want, (c, nch)

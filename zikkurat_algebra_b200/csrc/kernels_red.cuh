@@ -5,6 +5,7 @@
 #pragma once
 #include "ec_team.cuh"
 #include "msm_common.cuh"
+#include "red_plan.cuh"
 
 namespace zk {
 
@@ -173,53 +174,40 @@ ZK_D Xyzz<P> red_block_tree(const Team& tm, Xyzz<P> acc, int p, int tpo, XyzzMem
 // RC[window][0 .. NR) = rows, RC[window][NR .. NR + NC) = columns.
 template <class C>
 __global__ void __launch_bounds__(128)
-k_red_rowcol(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices, size_t slice_stride, int hr, int hc,
-             int tpo_r, int tpo_c, unsigned row_blocks, XyzzMem<typename C::Fp>* __restrict__ RC) {
+k_red_rowcol(const XyzzMem<typename C::Fp>* __restrict__ buckets, int nslices, size_t slice_stride, RedPlan pl,
+             XyzzMem<typename C::Fp>* __restrict__ RC) {
   using P = typename C::Fp;
   __shared__ XyzzMem<P> sm[32];
   const Team tm;
-  const int tq = threadIdx.x >> 2;
-  const uint32_t NR = 1u << hr, NC = 1u << hc;
-  const bool rows = blockIdx.x < row_blocks;
-  const int tpo = rows ? tpo_r : tpo_c;
-  const uint32_t o = (rows ? blockIdx.x : blockIdx.x - row_blocks) * (32 / tpo) + tq / tpo;   // output of this team
-  const int p = tq % tpo;
-  const uint32_t cnt = rows ? NC : NR;
-  const bool valid = o < (rows ? NR : NC);        // a block may have more teams than there are sums (tiny windows)
-  const XyzzMem<P>* b = buckets + (size_t)blockIdx.y * ((size_t)NR * NC) + (rows ? (size_t)o * NC : (size_t)o);
-  const size_t stride = rows ? 1 : NC;
+  const RedTask t = red_rowcol_task(pl, blockIdx.x, threadIdx.x >> 2);
+  const size_t NB = (size_t)1 << (pl.hr + pl.hc), nrc = ((size_t)1 << pl.hr) + ((size_t)1 << pl.hc);
+  const XyzzMem<P>* b = buckets + (size_t)blockIdx.y * NB + t.first;
   Xyzz<P> acc = xyzz_inf<P>();
-  for (uint32_t i = p; valid && i < cnt; i += tpo) {
+  for (uint32_t i = t.part; t.valid && i < t.entries; i += t.tpo) {
 #pragma unroll 1
-    for (int k = 0; k < nslices; k++) xyzz_add_tm<P>(tm, acc, load_xyzz<P>(b + (size_t)k * slice_stride + i * stride));
+    for (int k = 0; k < nslices; k++) xyzz_add_tm<P>(tm, acc, load_xyzz<P>(b + (size_t)k * slice_stride + (size_t)i * t.stride));
   }
-  acc = red_block_tree<P>(tm, acc, p, tpo, sm);
-  if (valid && p == 0 && tm.t == 0) store_xyzz<P>(RC + (size_t)blockIdx.y * (NR + NC) + (rows ? o : NR + o), acc);
+  acc = red_block_tree<P>(tm, acc, t.part, t.tpo, sm);
+  if (t.valid && t.part == 0 && tm.t == 0)
+    store_xyzz<P>(RC + (size_t)blockIdx.y * nrc + (t.rows ? t.out : ((size_t)1 << pl.hr) + t.out), acc);
 }
 // blockIdx.x = j: bit j of the column index (j < hc), bit j - hc of the row index (j < hc + hr), or the sum of all rows
 // (j = hc + hr); blockIdx.y = window.  T[window][j].
 template <class C>
 __global__ void __launch_bounds__(128)
-k_red_bits(const XyzzMem<typename C::Fp>* __restrict__ RC, int hr, int hc, XyzzMem<typename C::Fp>* __restrict__ T) {
+k_red_bits(const XyzzMem<typename C::Fp>* __restrict__ RC, RedPlan pl, XyzzMem<typename C::Fp>* __restrict__ T) {
   using P = typename C::Fp;
   __shared__ XyzzMem<P> sm[32];
   const Team tm;
   const int tq = threadIdx.x >> 2;
-  const uint32_t NR = 1u << hr, NC = 1u << hc;
+  const size_t nrc = ((size_t)1 << pl.hr) + ((size_t)1 << pl.hc);
   const int j = blockIdx.x;
-  const XyzzMem<P>* src = RC + (size_t)blockIdx.y * (NR + NC);
-  uint32_t cnt;
-  int bit = -1;
-  if (j < hc) { src += NR; cnt = NC >> 1; bit = j; }
-  else if (j < hc + hr) { cnt = NR >> 1; bit = j - hc; }
-  else cnt = NR;
+  const RedBits bt = red_bits_task(pl, j);
+  const XyzzMem<P>* src = RC + (size_t)blockIdx.y * nrc + bt.base;
   Xyzz<P> acc = xyzz_inf<P>();
-  for (uint32_t e = tq; e < cnt; e += 32) {
-    const uint32_t idx = bit < 0 ? e : (((e >> bit) << (bit + 1)) | (1u << bit) | (e & ((1u << bit) - 1u)));
-    xyzz_add_tm<P>(tm, acc, load_xyzz<P>(src + idx));
-  }
+  for (uint32_t e = tq; e < bt.entries; e += 32) xyzz_add_tm<P>(tm, acc, load_xyzz<P>(src + red_bit_member(e, bt.bit)));
   acc = red_block_tree<P>(tm, acc, tq, 32, sm);
-  if (tq == 0 && tm.t == 0) store_xyzz<P>(T + (size_t)blockIdx.y * (hr + hc + 1) + j, acc);
+  if (tq == 0 && tm.t == 0) store_xyzz<P>(T + (size_t)blockIdx.y * (pl.hr + pl.hc + 1) + j, acc);
 }
 // One block, NCH teams per window of the group.  The window sum  sum_b 2^b T_b + T_all  is a Horner chain over the bit
 // positions; NCH teams take NCH contiguous pieces of it at the same time (piece q covers bits [lo_q, hi_q), its value is
@@ -234,7 +222,8 @@ __global__ void k_tail_group_bits(const XyzzMem<typename C::Fp>* __restrict__ T,
   const Team tm;
   const int tq = threadIdx.x >> 2, w = tq / NCH, q = tq % NCH;
   const int nb = c - 1;                           // bit positions 0 .. nb-1
-  const int lo = (nb * q) / NCH, hi = (nb * (q + 1)) / NCH;
+  int lo, hi;
+  red_piece(nb, NCH, q, lo, hi);
   const XyzzMem<P>* t = T + (size_t)w * c;        // c - 1 bit sums and the plain sum
   if (w < Wg) {                                   // whole teams take the branch
     Xyzz<P> acc = xyzz_inf<P>();
@@ -251,7 +240,9 @@ __global__ void k_tail_group_bits(const XyzzMem<typename C::Fp>* __restrict__ T,
         acc = load_xyzz<P>(&Rw[tq + NCH - 1]);
 #pragma unroll 1
         for (int r = NCH - 2; r >= 0; r--) {
-          const int sh = (nb * (r + 1)) / NCH - (nb * r) / NCH;   // width of piece r: what is above it moves up by that much
+          int rlo, rhi;
+          red_piece(nb, NCH, r, rlo, rhi);
+          const int sh = rhi - rlo;                 // width of piece r: what is above it moves up by that much
 #pragma unroll 1
           for (int d = 0; d < sh; d++) acc = xyzz_dbl_team<P>(tm, acc);
           xyzz_add_tm<P>(tm, acc, load_xyzz<P>(&Rw[tq + r]));
@@ -279,12 +270,9 @@ __global__ void k_tail_group_bits(const XyzzMem<typename C::Fp>* __restrict__ T,
 template <class C>
 int launch_reduce_2d(cudaStream_t s, const XyzzMem<typename C::Fp>* buckets, int nslices, size_t slice_stride, int ns, int c, int extra,
                      XyzzMem<typename C::Fp>* RC, XyzzMem<typename C::Fp>* T, XyzzMem<typename C::Fp>* out) {
-  const int hc = c / 2, hr = c - 1 - hc;          // hc >= hr
-  auto tpo_of = [](uint32_t cnt) { uint32_t t = cnt / 8; return (int)(t < 1 ? 1 : (t > 32 ? 32 : t)); };
-  const int tpo_r = tpo_of(1u << hc), tpo_c = tpo_of(1u << hr);
-  const unsigned row_blocks = (unsigned)((((size_t)1 << hr) * tpo_r + 31) / 32), col_blocks = (unsigned)((((size_t)1 << hc) * tpo_c + 31) / 32);
-  k_red_rowcol<C><<<dim3(row_blocks + col_blocks, ns), 128, 0, s>>>(buckets, nslices, slice_stride, hr, hc, tpo_r, tpo_c, row_blocks, RC);
-  k_red_bits<C><<<dim3(c, ns), 128, 0, s>>>(RC, hr, hc, T);
+  const RedPlan pl = red_plan(c);
+  k_red_rowcol<C><<<dim3(pl.row_blocks + pl.col_blocks, ns), 128, 0, s>>>(buckets, nslices, slice_stride, pl, RC);
+  k_red_bits<C><<<dim3(c, ns), 128, 0, s>>>(RC, pl, T);
   // pieces per window: as many as fit into one block of 32 teams (a window's teams must share a warp: 8 teams)
   if (ns <= 8) k_tail_group_bits<C, 4><<<1, ((16 * ns + 31) / 32) * 32, 0, s>>>(T, ns, c, extra, out);
   else if (ns <= 16) k_tail_group_bits<C, 2><<<1, ((8 * ns + 31) / 32) * 32, 0, s>>>(T, ns, c, extra, out);
