@@ -583,6 +583,12 @@ def test_group_fft_next_row(zk, curve):
             f(m, refs.ptr(gen), refs.ptr(np.ascontiguousarray(proj).ravel()), refs.ptr(want.ravel()))
             got = zk.group_fft(curve, m, gen, proj, inverse=inverse)
             assert got.tobytes() == want.tobytes(), (m, inverse)
+            zk.set_glv(0)                       # twiddle products without the endomorphism split: same bytes
+            try:
+                got = zk.group_fft(curve, m, gen, proj, inverse=inverse)
+            finally:
+                zk.set_glv(1)
+            assert got.tobytes() == want.tobytes(), (m, inverse, "no glv")
         fwd = zk.group_fft(curve, m, gen, proj)
         back = zk.group_fft(curve, m, gen, fwd, inverse=True)
         assert zk.batch_to_affine(curve, back, "proj").tobytes() == aff.tobytes(), m

@@ -17,6 +17,7 @@
 
 #include "ec_team.cuh"
 #include "gfft.cuh"
+#include "glv.cuh"
 #include "msm_common.cuh"
 #include "ntt.cuh"
 
@@ -47,6 +48,47 @@ __device__ __noinline__ Xyzz<P> xyzz_scalar_mul(const Team& tm, const Xyzz<P>& p
   return acc;
 }
 
+// The same product through the curve endomorphism (G1 only, glv.cuh): k = k1 + k2 lambda with |k1|, |k2| < 2^127, so
+// k p = k1 p + k2 phi(p) by ONE joint chain of 128 doublings over 2-bit windows of both halves (table i p1 + j p2,
+// i, j < 4) instead of 256 doublings.  Same group element; precondition and switch as for the MSM (zkb200_set_glv).
+template <class C>
+__device__ __noinline__ Xyzz<typename C::Fp> xyzz_scalar_mul_glv(const Team& tm, const Xyzz<typename C::Fp>& p, const uint32_t* k) {
+  using P = typename C::Fp;
+  using G = typename GlvOf<C>::type;
+  uint32_t k1[4], k2[4];
+  bool n1, n2;
+  glv_decompose<G>(k, k1, n1, k2, n2);
+  Xyzz<P> tab[16];
+  tab[0] = xyzz_inf<P>();
+  tab[1] = p;
+  tab[4] = p;
+  tab[4].X = glv_beta_x<P, G>(p.X);                // phi(x, y) = (beta x, y); x = X / ZZ
+  if (n1) tab[1].Y = fe_neg<P>(tab[1].Y);
+  if (n2) tab[4].Y = fe_neg<P>(tab[4].Y);
+  tab[2] = tab[1]; gf_dbl<P>(tm, tab[2]);
+  tab[3] = tab[2]; gf_add<P>(tm, tab[3], tab[1]);
+  tab[8] = tab[4]; gf_dbl<P>(tm, tab[8]);
+  tab[12] = tab[8]; gf_add<P>(tm, tab[12], tab[4]);
+  for (int j = 1; j < 4; j++)
+    for (int i = 1; i < 4; i++) { tab[4 * j + i] = tab[4 * j]; gf_add<P>(tm, tab[4 * j + i], tab[i]); }
+  Xyzz<P> acc = xyzz_inf<P>();
+  for (int w = 63; w >= 0; w--) {
+    gf_dbl<P>(tm, acc);                             // no-ops while acc is infinity
+    gf_dbl<P>(tm, acc);
+    const int sh = (w & 15) * 2;
+    const uint32_t idx = (((k2[w >> 4] >> sh) & 3u) << 2) | ((k1[w >> 4] >> sh) & 3u);
+    if (idx) gf_add<P>(tm, acc, tab[idx]);
+  }
+  return acc;
+}
+template <class C>
+__device__ __forceinline__ Xyzz<typename C::Fp> gfft_scalar_mul(const Team& tm, const Xyzz<typename C::Fp>& p, const uint32_t* k, int glv) {
+  if constexpr (GlvOf<C>::available) {
+    if (glv) return xyzz_scalar_mul_glv<C>(tm, p, k);
+  }
+  return xyzz_scalar_mul<typename C::Fp>(tm, p, k);
+}
+
 __device__ __forceinline__ size_t gfft_bitrev(size_t x, int bits) {
   return bits == 0 ? 0 : (size_t)(__brevll((unsigned long long)x) >> (64 - bits));
 }
@@ -67,7 +109,7 @@ __global__ void __launch_bounds__(128) k_gfft_load(const uint32_t* __restrict__ 
 // stage s (1-based): butterflies at distance 2^(s-1) inside blocks of 2^s
 template <class C>
 __global__ void __launch_bounds__(128)
-k_gfft_stage(XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restrict__ table, int m, int s, int inverse) {
+k_gfft_stage(XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restrict__ table, int m, int s, int inverse, int glv) {
   using P = typename C::Fp;
   using F = typename C::Fr;
   size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // butterfly of this team
@@ -84,7 +126,7 @@ k_gfft_stage(XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restr
     for (int k = 0; k < 8; k++) w.l[k] = tw[k];
     if (inverse) w = fe_neg<F>(w);                 // w^-idx = -w^(N/2 - idx)
     w = fe_from_mont<F>(w);                        // plain integer for the scalar multiplication
-    b = xyzz_scalar_mul<P>(tm, b, w.l);
+    b = gfft_scalar_mul<C>(tm, b, w.l, glv);
   }
   Xyzz<P> nb = b;
   nb.Y = fe_neg<P>(b.Y);
@@ -99,7 +141,7 @@ k_gfft_stage(XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restr
 // optional scaling by N^-1 (inverse transform), then normalised projective output
 template <class C>
 __global__ void __launch_bounds__(128)
-k_gfft_store(const XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restrict__ table, int m, int scale,
+k_gfft_store(const XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* __restrict__ table, int m, int scale, int glv,
              uint32_t* __restrict__ dst) {
   using P = typename C::Fp;
   using F = typename C::Fr;
@@ -113,7 +155,7 @@ k_gfft_store(const XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* _
     const uint32_t* q = table + ((size_t)1 << (m - 1)) * 8;
     for (int k = 0; k < 8; k++) ninv.l[k] = q[k];
     ninv = fe_from_mont<F>(ninv);
-    a = xyzz_scalar_mul<P>(tm, a, ninv.l);
+    a = gfft_scalar_mul<C>(tm, a, ninv.l, glv);
   }
   if (tm.t != 0) return;
   uint32_t* o = dst + i * 3 * L;
@@ -127,20 +169,20 @@ k_gfft_store(const XyzzMem<typename C::Fp>* __restrict__ data, const uint32_t* _
 
 template <class C>
 void gfft_device(cudaStream_t s, int m, const uint32_t* d_gen, const uint32_t* d_src, void* d_work, uint32_t* d_table,
-                 uint32_t* d_dst, int inverse, int jac) {
+                 uint32_t* d_dst, int inverse, int jac, int glv) {
   using Mem = XyzzMem<typename C::Fp>;
   const size_t N = (size_t)1 << m;
   Mem* data = (Mem*)d_work;
   ntt_build_table<typename C::Fr>(s, d_gen, N >> 1, m, d_table);
   k_gfft_load<C><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(d_src, m, jac, data);
   for (int st = 1; st <= m; st++)
-    k_gfft_stage<C><<<(unsigned)((4 * (N >> 1) + 127) / 128), 128, 0, s>>>(data, d_table, m, st, inverse);
-  k_gfft_store<C><<<(unsigned)((4 * N + 127) / 128), 128, 0, s>>>(data, d_table, m, inverse, d_dst);
+    k_gfft_stage<C><<<(unsigned)((4 * (N >> 1) + 127) / 128), 128, 0, s>>>(data, d_table, m, st, inverse, glv);
+  k_gfft_store<C><<<(unsigned)((4 * N + 127) / 128), 128, 0, s>>>(data, d_table, m, inverse, glv, d_dst);
 }
 
-template void gfft_device<Bn254>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
-template void gfft_device<Bls12381>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
-template void gfft_device<Bn254G2>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
-template void gfft_device<Bls12381G2>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int);
+template void gfft_device<Bn254>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int, int);
+template void gfft_device<Bls12381>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int, int);
+template void gfft_device<Bn254G2>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int, int);
+template void gfft_device<Bls12381G2>(cudaStream_t, int, const uint32_t*, const uint32_t*, void*, uint32_t*, uint32_t*, int, int, int);
 
 }  // namespace zk

@@ -9,6 +9,7 @@ namespace zk {
 // records (4L words each), d_table (N/2 + 1) * 8 words, d_gen 8 words (Montgomery Fr generator of the order-N subgroup)
 template <class C>
 void gfft_device(cudaStream_t s, int m, const uint32_t* d_gen, const uint32_t* d_src, void* d_work, uint32_t* d_table,
-                 uint32_t* d_dst, int inverse, int jac);
+                 uint32_t* d_dst, int inverse, int jac, int glv);
+// glv != 0: twiddle products through the curve endomorphism where the curve has one (G1; subgroup points, see glv.cuh)
 
 }  // namespace zk

@@ -1380,7 +1380,7 @@ void run_gfft(int m, const uint64_t* gen, const uint64_t* src, uint64_t* tgt, in
   host_to_device(cx, d_src, src, bytes, s);
   g_launches += 3 + m;
   CK(cudaEventRecord(cx.ev[0], s));
-  gfft_device<C>(s, m, d_gen, d_src, d_work, d_table, d_dst, inverse, jac);
+  gfft_device<C>(s, m, d_gen, d_src, d_work, d_table, d_dst, inverse, jac, glv_enabled() ? 1 : 0);
   CK(cudaGetLastError());
   CK(cudaEventRecord(cx.ev[1], s));
   CK(cudaMemcpyAsync(tgt, d_dst, bytes, cudaMemcpyDeviceToHost, s));
