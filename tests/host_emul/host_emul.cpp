@@ -57,6 +57,8 @@ static Xyzz<P> sum_list(long n, const uint64_t* pts, const uint8_t* neg) {
     st<C::Fp>(t, fe_mul2<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b), ld<C::Fp>(c), ld<C::Fp>(d))); }                       \
   extern "C" void he_##NAME##_fp_mul_pair(const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* t1, uint64_t* t2) { \
     FePair<C::Fp> r = fe_mul_pair_call<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b), ld<C::Fp>(c)); st<C::Fp>(t1, r.u); st<C::Fp>(t2, r.v); } \
+  extern "C" void he_##NAME##_fp_mul_kara(const uint64_t* a, const uint64_t* b, uint64_t* t) {                  \
+    Fe<C::Fp> x = ld<C::Fp>(a), y = ld<C::Fp>(b), r; mont_mul_kara_limbs<C::Fp>(r.l, x.l, y.l); st<C::Fp>(t, r); }  \
   extern "C" void he_##NAME##_fp_sqr(const uint64_t* a, uint64_t* t) { st<C::Fp>(t, fe_sqr<C::Fp>(ld<C::Fp>(a))); }  \
   extern "C" void he_##NAME##_fp_add(const uint64_t* a, const uint64_t* b, uint64_t* t) {                       \
     st<C::Fp>(t, fe_add<C::Fp>(ld<C::Fp>(a), ld<C::Fp>(b))); }                                                  \

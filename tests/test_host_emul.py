@@ -134,6 +134,31 @@ def test_fp_paired_products(he, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_fp_karatsuba_product(he, curve):
+    """mont_mul_kara_limbs (fp.cuh): one Karatsuba level + separate word-serial reduction == the Montgomery product."""
+    cv = pyec.CURVES[curve]
+    L = cv.nlimbs_p
+    rng = random.Random(44)
+    f = getattr(he, f"he_{curve}_fp_mul_kara")
+    f.argtypes = [refs.U64P] * 3
+    f.restype = None
+    Rinv = pow(cv.R, -1, cv.p)
+    half = 1 << (32 * L)            # the two halves of an operand: equal halves, a0 < a1, a0 > a1, all-ones halves
+    edge = [0, 1, cv.p - 1, cv.p - 2, (1 << (64 * L - 3)) % cv.p, cv.R % cv.p, (1 << 32) - 1, (cv.p - 1) >> 1,
+            (half - 1), (half - 1) * half % cv.p, (half + 1) % cv.p, (5 * half + 5) % cv.p, (7 * half + 3) % cv.p, (3 * half + 7) % cv.p]
+    pairs = [(a, b) for a in edge for b in edge]
+    pairs += [(rng.randrange(cv.p), rng.randrange(cv.p)) for _ in range(6000)]
+    pairs += [(cv.p - 1 - rng.randrange(1 << 40), cv.p - 1 - rng.randrange(1 << 40)) for _ in range(500)]
+    pairs += [(rng.randrange(1 << 70), rng.randrange(cv.p)) for _ in range(500)]
+    pairs += [((rng.randrange(1 << 64) * half + rng.randrange(1 << 64)) % cv.p, rng.randrange(cv.p)) for _ in range(500)]
+    for a, b in pairs:
+        arrs = [_arr(x.to_bytes(8 * L, "little")) for x in (a, b)]
+        out = np.zeros(L, np.uint64)
+        f(*[refs.ptr(x) for x in arrs], refs.ptr(out))
+        assert int.from_bytes(out.tobytes(), "little") == a * b * Rinv % cv.p, (hex(a), hex(b))
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_fp_mul_matches_oracle_bytes(he, curve):
     L = refs.CURVE_LIMBS[curve]
     cv = pyec.CURVES[curve]

@@ -175,6 +175,139 @@ ZK_HD void mont_mul_pair_limbs(uint32_t* r1, uint32_t* r2, const uint32_t* a, co
   mont_mul_finish<P>(r2, ((L - 1) & 1) ? B2 : A2, ((L - 1) & 1) ? A2 : B2);
 }
 
+// ---- Karatsuba form of the product (experiment, see profiles/r2_notes.md section 16) ---------------------------------
+// Every instruction that yields the high half of a 32x32-bit product occupies the IMAD pipe for 4 cycles; additions run on the
+// other pipe.  One Karatsuba level computes the 2L-limb product a*b from three (L/2)^2 products instead of L^2 (108 instead of
+// 144 for 12 limbs) at the price of ~140 additions, and a separate word-serial Montgomery reduction (L^2 + L products) follows.
+// mul_wide_limbs: plain product of two H-limb numbers, the even/odd row scheme of mont_mul_limbs without the reduction
+// (limb i of the result is final after row i).
+template <int H>
+ZK_HD void mul_wide_limbs(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  static_assert(H % 2 == 0 && H >= 2, "even limb count expected");
+  uint32_t A[H], B[H];
+#pragma unroll
+  for (int j = 0; j < H; j += 2) {
+    A[j] = mul_lo(a[j], b[0]);
+    A[j + 1] = mul_hi(a[j], b[0]);
+    B[j] = mul_lo(a[j + 1], b[0]);
+    B[j + 1] = mul_hi(a[j + 1], b[0]);
+  }
+  t[0] = A[0];
+#pragma unroll
+  for (int i = 1; i < H; i++) {
+    uint32_t* E = (i & 1) ? B : A;
+    uint32_t* O = (i & 1) ? A : B;
+    E[0] = add_cc(E[0], O[1]);
+#pragma unroll
+    for (int j = 0; j < H - 2; j += 2) {
+      O[j] = madc_lo_cc(a[j + 1], b[i], O[j + 2]);
+      O[j + 1] = madc_hi_cc(a[j + 1], b[i], O[j + 3]);
+    }
+    O[H - 2] = madc_lo_cc(a[H - 1], b[i], 0u);
+    O[H - 1] = madc_hi(a[H - 1], b[i], 0u);
+    cmad_row<H, false>(E, a, b[i]);
+    O[H - 1] = addc(O[H - 1], 0u);
+    t[i] = E[0];
+  }
+  const uint32_t* E = ((H - 1) & 1) ? B : A;
+  const uint32_t* O = ((H - 1) & 1) ? A : B;
+  t[H] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 1; k < H - 1; k++) t[H + k] = addc_cc(E[k + 1], O[k]);
+  t[2 * H - 1] = addc(O[H - 1], 0u);
+}
+// d = |x - y| (H limbs), returns all-ones when x < y
+template <int H>
+ZK_HD uint32_t abs_diff_limbs(uint32_t* d, const uint32_t* x, const uint32_t* y) {
+  d[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+  for (int i = 1; i < H; i++) d[i] = subc_cc(x[i], y[i]);
+  const uint32_t s = subc(0u, 0u);
+  d[0] = sub_cc(d[0] ^ s, s);
+#pragma unroll
+  for (int i = 1; i < H - 1; i++) d[i] = subc_cc(d[i] ^ s, s);
+  d[H - 1] = subc(d[H - 1] ^ s, s);
+  return s;
+}
+// T (2L limbs) = a * b:  a = a0 + a1 B, b = b0 + b1 B (B = 2^(16 L)),  a0 b1 + a1 b0 = a0 b0 + a1 b1 + (a0 - a1)(b1 - b0)
+template <int L>
+ZK_HD void kara_mul_limbs(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+  constexpr int H = L / 2;
+  uint32_t da[H], db[H], zm[2 * H], z1[2 * H + 1];
+  const uint32_t sa = abs_diff_limbs<H>(da, a, a + H);
+  const uint32_t sb = abs_diff_limbs<H>(db, b + H, b);
+  mul_wide_limbs<H>(T, a, b);
+  mul_wide_limbs<H>(T + 2 * H, a + H, b + H);
+  mul_wide_limbs<H>(zm, da, db);
+  const uint32_t neg = sa ^ sb;          // (a0 - a1)(b1 - b0) < 0
+  z1[0] = add_cc(T[0], T[2 * H]);
+#pragma unroll
+  for (int k = 1; k < 2 * H; k++) z1[k] = addc_cc(T[k], T[2 * H + k]);
+  z1[2 * H] = addc(0u, 0u);
+  (void)add_cc(neg, neg);                // carry = 1 when zm is subtracted (two's complement: + ~zm + 1)
+#pragma unroll
+  for (int k = 0; k < 2 * H; k++) z1[k] = addc_cc(z1[k], zm[k] ^ neg);
+  z1[2 * H] = addc(z1[2 * H], neg);
+  T[H] = add_cc(T[H], z1[0]);
+#pragma unroll
+  for (int k = 1; k <= 2 * H; k++) T[H + k] = addc_cc(T[H + k], z1[k]);
+#pragma unroll
+  for (int k = 3 * H + 1; k < 4 * H - 1; k++) T[k] = addc_cc(T[k], 0u);
+  T[4 * H - 1] = addc(T[4 * H - 1], 0u);
+}
+// r = T / R mod p for a 2L-limb T < p * R: word-serial reduction of the low half (rows of m * p in the even/odd scheme),
+// plus the high half, one conditional subtraction.
+template <class P>
+ZK_HD void mont_redc_limbs(uint32_t* r, const uint32_t* T) {
+  constexpr int L = P::L;
+  uint32_t A[L], B[L];
+#pragma unroll
+  for (int k = 0; k < L; k++) A[k] = T[k];
+  {
+    const uint32_t m = mul_lo(A[0], P::INV);
+#pragma unroll
+    for (int j = 0; j < L; j += 2) {
+      B[j] = mul_lo(P::mod(j + 1), m);
+      B[j + 1] = mul_hi(P::mod(j + 1), m);
+    }
+    cmad_row_const<L>(A, ModRow<P, 0>(), m);
+    B[L - 1] = addc(B[L - 1], 0u);
+  }
+#pragma unroll
+  for (int i = 1; i < L; i++) {
+    uint32_t* E = (i & 1) ? B : A;
+    uint32_t* O = (i & 1) ? A : B;
+    E[0] = add_cc(E[0], O[1]);
+    const uint32_t m = mul_lo(E[0], P::INV);
+#pragma unroll
+    for (int j = 0; j < L - 2; j += 2) {
+      O[j] = madc_lo_cc(P::mod(j + 1), m, O[j + 2]);
+      O[j + 1] = madc_hi_cc(P::mod(j + 1), m, O[j + 3]);
+    }
+    O[L - 2] = madc_lo_cc(P::mod(L - 1), m, 0u);
+    O[L - 1] = madc_hi(P::mod(L - 1), m, 0u);
+    cmad_row_const<L>(E, ModRow<P, 0>(), m);
+    O[L - 1] = addc(O[L - 1], 0u);
+  }
+  const uint32_t* E = ((L - 1) & 1) ? B : A;
+  const uint32_t* O = ((L - 1) & 1) ? A : B;
+  r[0] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 1; k < L - 1; k++) r[k] = addc_cc(E[k + 1], O[k]);
+  r[L - 1] = addc(O[L - 1], 0u);
+  r[0] = add_cc(r[0], T[L]);
+#pragma unroll
+  for (int k = 1; k < L - 1; k++) r[k] = addc_cc(r[k], T[L + k]);
+  r[L - 1] = addc(r[L - 1], T[2 * L - 1]);
+  final_sub<P>(r);
+}
+template <class P>
+ZK_HD void mont_mul_kara_limbs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t T[2 * P::L];
+  kara_mul_limbs<P::L>(T, a, b);
+  mont_redc_limbs<P>(r, T);
+}
+
 // Fused r = (a*b + c*d) * R^-1 mod p with ONE interleaved reduction: 3L^2 + L products instead of the
 // 4L^2 + 2L of two separate multiplications (used for Y3 = R*(Q-X3) + (-Y1)*PPP in every group addition).
 // Inputs canonical.  Row bound: T_i < 3p(1 + 2^-32), and T + 3*2^32*p < 2^(32(L+1)) needs 3p < 2^(32L)
@@ -326,10 +459,16 @@ ZK_HD Fe<P> fe_sqr(const Fe<P>& a) {
 // Operands travel in registers (no stack traffic); used where the fully inlined group operation would
 // not fit the instruction cache (k_accumulate: 10 multiplications per insertion).
 #if defined(__CUDACC__)
+// Build-time experiment switch (tools/build_variant.py ... -DZK_KARA=1): the out-of-line general products of 12-limb fields
+// through mont_mul_kara_limbs.
+#ifndef ZK_KARA
+#define ZK_KARA 0
+#endif
 template <class P>
 __device__ __noinline__ Fe<P> fe_mul_call(Fe<P> a, Fe<P> b) {
   Fe<P> r;
-  mont_mul_limbs<P>(r.l, a.l, b.l);
+  if constexpr (ZK_KARA && P::L >= 12) mont_mul_kara_limbs<P>(r.l, a.l, b.l);
+  else mont_mul_limbs<P>(r.l, a.l, b.l);
   return r;
 }
 template <class P>
@@ -341,7 +480,12 @@ struct FePair { Fe<P> u, v; };
 template <class P>
 __device__ __noinline__ FePair<P> fe_mul_pair_call(Fe<P> a, Fe<P> b, Fe<P> c) {
   FePair<P> r;
-  mont_mul_pair_limbs<P>(r.u.l, r.v.l, a.l, b.l, c.l);
+  if constexpr (ZK_KARA && P::L >= 12) {
+    mont_mul_kara_limbs<P>(r.u.l, a.l, b.l);
+    mont_mul_kara_limbs<P>(r.v.l, a.l, c.l);
+  } else {
+    mont_mul_pair_limbs<P>(r.u.l, r.v.l, a.l, b.l, c.l);
+  }
   return r;
 }
 template <class P>
