@@ -96,7 +96,10 @@ void bls12_381_G2_proj_MSM_mont_coeff_affine_out(int npoints, const uint64_t *ex
  * reference (lib/cbits/curves/g1/proj/bn128_G1_proj.h:48-49, definitions bn128_G1_proj.c:678-789 and twin):
  * src, tgt = 2^m projective points, gen = Montgomery-form generator of the order-2^m subgroup of Fr.
  * forward: tgt[k] = sum_j gen^(jk) * src[j]; inverse: tgt[j] = 2^-m sum_k gen^(-jk) * src[k]; the results are
- * normalised ((x, y, 1) / (0, 1, 0)) like the reference's, hence bit-identical. */
+ * normalised ((x, y, 1) / (0, 1, 0)) like the reference's, hence bit-identical.
+ * The G1 twiddle products use the same endomorphism split as the MSM (k = k1 + k2 lambda, 128 instead of 256 doublings) and
+ * therefore share its precondition and its switch: input points in the prime-order subgroup, zkb200_set_glv(0) / $ZKB200_GLV=0
+ * for arbitrary curve points (see zkb200_set_glv below).  G2 is not affected. */
 void bn128_G1_proj_fft_forward    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
 void bn128_G1_proj_fft_inverse    (int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
 void bls12_381_G1_proj_fft_forward(int m, const uint64_t *gen, const uint64_t *src, uint64_t *tgt);
@@ -190,7 +193,8 @@ void zkb200_srs_cache_drop(void);
  * so a caller that feeds curve points OUTSIDE the subgroup (the reference multiplies them by the integer scalar like
  * any other point: it validates nothing) must switch the split off to get the reference's answer.
  * G1 elements of an SRS, commitments, proofs -- everything a KZG prover handles -- are subgroup points.
- * tests/test_configs_gpu.py::test_glv_precondition_and_switch shows both sides. */
+ * tests/test_configs_gpu.py::test_glv_precondition_and_switch shows both sides.  The switch also governs the twiddle products
+ * of the G1 group FFT (scope row 8f.4 above). */
 void zkb200_set_glv(int on);
 
 /* Give back all device memory this library holds on every device it has used (work arrays that only grow otherwise,
